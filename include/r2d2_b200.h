@@ -1,0 +1,195 @@
+/* libr2d2_b200 - C ABI of the B200-native learner hot path of pytorch-r2d2-DPG.
+ *
+ * The reference (pure Python) has no FFI; its boundary for this path is the module surface
+ * learner.py / replay_memory.py / models.py / utils.py.  Each entry point below replaces the
+ * reference function(s) cited next to it; the host-side mirror in pytorch-r2d2-dpg_b200/*.py binds
+ * them with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; r2d2_last_error() (thread-local) has the text;
+ *   - tensors are caller-owned device memory (fp32, contiguous, time-major [T,B,*] as produced by
+ *     replay_memory.py:123-136), passed as raw pointers + explicit sizes; no torch types here;
+ *   - the library owns only opaque handles (replay shard + sum tree, learner workspaces);
+ *   - every launch goes to the cudaStream_t given (passed as void*); nothing synchronises the host
+ *     unless stated; one host thread per handle.
+ *   - parameter blocks are FLAT fp32 buffers in the reference's state_dict order
+ *     (l1.weight[H,I], l1.bias[H], l2.weight_ih[4H,H], l2.weight_hh[4H,H], l2.bias_ih[4H],
+ *      l2.bias_hh[4H], l3.weight[A,H], l3.bias[A]; models.py:17-19,59-61), I = O (actor) or O+A (critic).
+ */
+#ifndef R2D2_B200_H_
+#define R2D2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R2D2_OK 0
+#define R2D2_ERR_CUDA (-1)
+#define R2D2_ERR_ARG (-2)
+#define R2D2_ERR_UNSUPPORTED (-3)
+#define R2D2_ERR_STATE (-4)
+
+typedef void* r2d2_stream_t; /* cudaStream_t */
+
+int r2d2_version(void);                /* 100 * major + minor */
+const char* r2d2_arch(void);           /* "sm_100a" */
+const char* r2d2_last_error(void);
+int r2d2_device_sm_count(int* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense building block (x*W^T, dgrad, wgrad of models.py:33,37-39,76,80-82): fp32 in/out, bf16x3
+ * tensor-core MMAs.  layout: 0 = NT (A[M,K] * B[N,K]^T), 1 = NN (A[M,K] * B[K,N]), 2 = TN (A[K,M]^T * B[K,N]).
+ * epilogue: 0 none, 1 tanh(acc+bias), 2 (acc+bias)*(1-Z^2), 3 acc+bias+Z.  split_k > 1 adds into C.
+ * ---------------------------------------------------------------------------------------------- */
+int r2d2_gemm_f32(int layout, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                  const float* A2, long long lda2, const float* B2, long long ldb2, int K2, float* C,
+                  long long ldc, const float* bias, const float* Z, long long ldz, int epilogue, int split_k,
+                  r2d2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Recurrent net chains: replace the per-timestep python loops over ActorNet/CriticNet.__call__
+ * (models.py:32-40,74-83) at learner.py:92-95,102-106,120-123.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int obs_size;   /* O */
+  int n_actions;  /* A */
+  int hidden;     /* H (128 in the reference, models.py:17-19) */
+  int is_critic;  /* 0: ActorNet, 1: CriticNet (input = cat(obs, action), head without tanh, A outputs) */
+} r2d2_net_shape;
+
+size_t r2d2_net_param_count(const r2d2_net_shape* shape);
+/* floats of workspace needed by one chain of T input rows, `repeat` cell steps per row, batch B */
+size_t r2d2_net_workspace_floats(const r2d2_net_shape* shape, int T, int B, int repeat);
+
+/* Forward over T rows (S = T*repeat cell steps).  obs [T,B,O]; act [T,B,A] (critic only, else NULL);
+ * h0/c0 [B,H] or NULL for the zero state (models.py:34-36).  Head outputs are produced for input rows
+ * [head_first_row, T) (after the last of the `repeat` steps of each row) into out [(T-head_first_row),B,A].
+ * workspace keeps the activations for r2d2_lstm_net_backward. */
+int r2d2_lstm_net_forward(const r2d2_net_shape* shape, const float* params, const float* obs, const float* act,
+                          const float* h0, const float* c0, int T, int B, int repeat, int head_first_row,
+                          float* out, float* workspace, r2d2_stream_t stream);
+
+/* BPTT through the chain saved in `workspace`.  d_out [(T-head_first_row),B,A] = dLoss/d(head output).
+ * grads: flat buffer like params, ACCUMULATED into (zero it first); NULL -> data gradient only.
+ * d_act [T,B,A]: dLoss/d(action input) (critic only, optional).  The workspace is consumed. */
+int r2d2_lstm_net_backward(const r2d2_net_shape* shape, const float* params, const float* obs, const float* act,
+                           const float* d_out, int T, int B, int repeat, int head_first_row, float* grads,
+                           float* d_act, float* workspace, r2d2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused n-step target + value rescaling + TD loss gradient + sequence priority
+ * (learner.py:107-111,135-138; utils.py:17-21).  q, q_next [L,B,A]; rew, term [T',B].
+ * Any output pointer may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int r2d2_td_priority(const float* q, const float* q_next, const float* rew, const float* term, int L, int B,
+                     int A, int burn_in, int n_step, float gamma, float eta, float* target, float* dq,
+                     float* td_sq, float* priority, float* critic_loss, r2d2_stream_t stream);
+
+/* torch.optim.Adam defaults (learner.py:50-53,114,128) on a flat buffer; grad is multiplied by grad_scale first. */
+int r2d2_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step,
+                   float lr, float beta1, float beta2, float eps, float grad_scale, r2d2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GPU-resident prioritized sequence replay (replaces LearnerReplayMemory, replay_memory.py:67-175).
+ * Rows of all episodes live in HBM (SoA); one sum-tree leaf per row (priority 0 for rows that are
+ * not valid sequence starts); 32-ary tree of fp32 partial sums.  P(start) is proportional to its
+ * priority, which is what the reference's two-level draw (replay_memory.py:95-114) samples.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct r2d2_replay r2d2_replay_t;
+
+typedef struct {
+  int obs_size, n_actions, hidden;
+  int burn_in, learning, n_step;   /* window rows T' = burn_in + learning + n_step (replay_memory.py:116) */
+  long long capacity_rows;         /* physical rows in HBM (ring) */
+  long long max_sequences;         /* eviction threshold on the sequence counter (replay_memory.py:148) */
+} r2d2_replay_config;
+
+int r2d2_replay_create(r2d2_replay_t** out, const r2d2_replay_config* cfg);
+int r2d2_replay_destroy(r2d2_replay_t* r);
+
+/* Append one episode (replay_memory.py:141-152).  HOST pointers: obs [n_rows,O], act [n_rows,A], rew [n_rows],
+ * term [n_rows] (n_rows includes the n_step pad rows, actor.py:173), states [n_state_rows,4,2,H]
+ * (actor, target_actor, critic, target_critic) x (hx,cx), priority [n_starts].  Oldest episodes are
+ * evicted FIFO when the ring or max_sequences overflows.  Synchronises the stream. */
+int r2d2_replay_add_episode(r2d2_replay_t* r, const float* obs, const float* act, const float* rew,
+                            const float* term, const float* states, int n_rows, int n_state_rows,
+                            const float* priority, int n_starts, r2d2_stream_t stream);
+
+/* Draw `batch` starts from DEVICE uniforms u[batch] in [0,1) and gather the time-major batch:
+ * leaf_idx [batch] (int64, start row = tree leaf), obs [T',batch,O], act [T',batch,A], rew [T',batch],
+ * term [T',batch], states [4,2,batch,H].  Any gather output may be NULL. */
+int r2d2_replay_sample(r2d2_replay_t* r, const float* u, int batch, long long* leaf_idx, float* obs, float* act,
+                       float* rew, float* term, float* states, r2d2_stream_t stream);
+
+/* priority[leaf_idx[i]] = prio[i] (DEVICE arrays; on duplicates the highest i wins, like the python
+ * loop at learner.py:136-139) and recompute the touched tree paths. */
+int r2d2_replay_update_priorities(r2d2_replay_t* r, const long long* leaf_idx, const float* prio, int batch,
+                                  r2d2_stream_t stream);
+
+typedef struct {
+  long long n_episodes, n_rows_used, sequence_counter, capacity_rows, tree_levels, tree_nodes;
+  double total_priority;
+} r2d2_replay_stats_t;
+int r2d2_replay_stats(r2d2_replay_t* r, r2d2_replay_stats_t* out, r2d2_stream_t stream); /* synchronises */
+
+/* host-side decode of a start row into the reference's (episode_index, sequence_index) pair
+ * (position of the episode in FIFO order, offset inside it); -1/-1 if the row is not live. */
+int r2d2_replay_decode(r2d2_replay_t* r, const long long* leaf_idx_host, int n, long long* episode_index,
+                       long long* sequence_index);
+/* raw device views for tests: tree level pointer/size, leaf priorities */
+int r2d2_replay_tree_level(r2d2_replay_t* r, int level, const float** dev_ptr, long long* n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Learner iteration engine (learner.py:84-139 minus file I/O).  Parameters, gradients and Adam
+ * moments are caller-owned flat device buffers; the engine owns batch buffers and workspaces.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct r2d2_learner r2d2_learner_t;
+
+typedef struct {
+  int obs_size, n_actions, hidden;
+  int batch, burn_in, learning, n_step;
+  float gamma, actor_lr, critic_lr, eta;
+  int target_update_interval;      /* learner.py:45,131 */
+  float* actor_params;  float* critic_params;  float* target_actor_params;  float* target_critic_params;
+  float* actor_grads;   float* critic_grads;
+  float* actor_exp_avg; float* actor_exp_avg_sq; float* critic_exp_avg; float* critic_exp_avg_sq;
+} r2d2_learner_config;
+
+typedef struct {
+  /* device pointers into the engine-owned batch (fill them via r2d2_replay_sample or memcpy) */
+  float* obs;      /* [T',B,O] */
+  float* act;      /* [T',B,A] */
+  float* rew;      /* [T',B]   */
+  float* term;     /* [T',B]   */
+  float* states;   /* [4,2,B,H] actor, target_actor, critic, target_critic */
+  long long* leaf_idx; /* [B] */
+  float* uniforms; /* [B] */
+  /* results of the last iteration */
+  float* q_value;        /* [L,B,A] */
+  float* target_q_value; /* [L,B,A] */
+  float* td_sq;          /* [L,B]   */
+  float* priority;       /* [B]     */
+  float* losses;         /* [2] critic_loss, actor_loss */
+} r2d2_learner_buffers;
+
+int r2d2_learner_create(r2d2_learner_t** out, const r2d2_learner_config* cfg);
+int r2d2_learner_destroy(r2d2_learner_t* l);
+int r2d2_learner_buffers_get(r2d2_learner_t* l, r2d2_learner_buffers* out);
+/* phase 1: target chains, online critic chain, TD/priority kernel, critic BPTT -> critic_grads */
+int r2d2_learner_critic_phase(r2d2_learner_t* l, r2d2_stream_t stream);
+/* phase 2: critic Adam (grads * grad_scale), actor chain (zero state, 2 cell steps/row), critic on
+ * actor actions, dgrad through critic, actor BPTT -> actor_grads */
+int r2d2_learner_actor_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t stream);
+/* phase 3: actor Adam, step counter, hard target update every target_update_interval steps */
+int r2d2_learner_finish_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t stream);
+int r2d2_learner_step_count(r2d2_learner_t* l);
+/* number of kernels launched by the three phases of one iteration (bench.py's gpu_launches) */
+int r2d2_learner_launches_per_iteration(r2d2_learner_t* l);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2D2_B200_H_ */

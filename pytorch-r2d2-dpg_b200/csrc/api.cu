@@ -1,0 +1,175 @@
+// extern "C" surface of libr2d2_b200 (declared in include/r2d2_b200.h).
+#include <atomic>
+
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "learner.cuh"
+#include "lstm_scan.cuh"
+#include "net.cuh"
+#include "replay.cuh"
+
+namespace r2d2 {
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error() { return g_last_error.c_str(); }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace r2d2
+
+using namespace r2d2;
+
+static inline cudaStream_t S(r2d2_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline NetShape shape_of(const r2d2_net_shape* s) {
+  return NetShape{s->obs_size, s->n_actions, s->hidden, s->is_critic != 0};
+}
+
+extern "C" {
+
+int r2d2_version(void) { return 100; }
+const char* r2d2_arch(void) { return "sm_100a"; }
+const char* r2d2_last_error(void) { return last_error(); }
+
+int r2d2_device_sm_count(int* out) {
+  R2D2_REQUIRE(out, "null");
+  int dev = 0;
+  R2D2_CUDA_TRY(cudaGetDevice(&dev));
+  R2D2_CUDA_TRY(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+  return R2D2_OK;
+}
+
+int r2d2_gemm_f32(int layout, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                  const float* A2, long long lda2, const float* B2, long long ldb2, int K2, float* C,
+                  long long ldc, const float* bias, const float* Z, long long ldz, int epilogue, int split_k,
+                  r2d2_stream_t stream) {
+  R2D2_REQUIRE(layout >= 0 && layout <= 2, "layout");
+  GemmParams p;
+  p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.A2 = A2; p.lda2 = lda2; p.B2 = B2; p.ldb2 = ldb2; p.K2 = K2;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.Z = Z; p.ldz = ldz; p.epilogue = epilogue;
+  p.split_k = split_k < 1 ? 1 : split_k;
+  return gemm_f32(p, (GemmLayout)layout, S(stream));
+}
+
+size_t r2d2_net_param_count(const r2d2_net_shape* shape) { return shape ? shape_of(shape).param_count() : 0; }
+
+size_t r2d2_net_workspace_floats(const r2d2_net_shape* shape, int T, int B, int repeat) {
+  return shape ? ChainWs::floats(shape_of(shape), T, B, repeat) : 0;
+}
+
+int r2d2_lstm_net_forward(const r2d2_net_shape* shape, const float* params, const float* obs, const float* act,
+                          const float* h0, const float* c0, int T, int B, int repeat, int head_first_row,
+                          float* out, float* workspace, r2d2_stream_t stream) {
+  R2D2_REQUIRE(shape && params && obs && workspace, "null");
+  R2D2_REQUIRE(T > 0 && B > 0 && repeat >= 1, "shape");
+  const NetShape s = shape_of(shape);
+  const NetParams P = NetParams::from_flat(const_cast<float*>(params), s);
+  const ChainWs ws = ChainWs::carve(workspace, s, T, B, repeat);
+  R2D2_TRY(net_forward(s, P, ws, obs, act, h0, c0, T, B, repeat, S(stream)));
+  if (out) {
+    float* ho = ws.head_out + (size_t)head_first_row * B * s.act;
+    R2D2_TRY(net_head_forward(s, P, ws, head_first_row, T, B, repeat, ho, s.act, S(stream)));
+    R2D2_CUDA_TRY(cudaMemcpyAsync(out, ho, sizeof(float) * (size_t)(T - head_first_row) * B * s.act,
+                                  cudaMemcpyDeviceToDevice, S(stream)));
+  }
+  return R2D2_OK;
+}
+
+int r2d2_lstm_net_backward(const r2d2_net_shape* shape, const float* params, const float* obs, const float* act,
+                           const float* d_out, int T, int B, int repeat, int head_first_row, float* grads,
+                           float* d_act, float* workspace, r2d2_stream_t stream) {
+  R2D2_REQUIRE(shape && params && obs && d_out && workspace, "null");
+  const NetShape s = shape_of(shape);
+  const NetParams P = NetParams::from_flat(const_cast<float*>(params), s);
+  const ChainWs ws = ChainWs::carve(workspace, s, T, B, repeat);
+  const long long n = (long long)(T - head_first_row) * B * s.act;
+  const float* d_pre = d_out;
+  if (!s.critic) {  // through the output tanh (models.py:39) using the head outputs kept by the forward call
+    R2D2_TRY(mul_dtanh(d_out, ws.head_out + (size_t)head_first_row * B * s.act, ws.d_pre, n, S(stream)));
+    d_pre = ws.d_pre;
+  }
+  NetParams G;
+  if (grads) G = NetParams::from_flat(grads, s);
+  return net_backward(s, P, grads ? &G : nullptr, ws, obs, act, d_pre, head_first_row, T, B, repeat, d_act, nullptr,
+                      S(stream));
+}
+
+int r2d2_td_priority(const float* q, const float* q_next, const float* rew, const float* term, int L, int B,
+                     int A, int burn_in, int n_step, float gamma, float eta, float* target, float* dq,
+                     float* td_sq, float* priority, float* critic_loss, r2d2_stream_t stream) {
+  TdPriorityParams p;
+  p.q = q; p.q_next = q_next; p.rew = rew; p.term = term; p.target = target; p.dq = dq; p.td_sq = td_sq;
+  p.priority = priority; p.loss_sum = critic_loss; p.L = L; p.B = B; p.A = A; p.burn_in = burn_in; p.n_step = n_step;
+  p.gamma_n = (float)pow((double)gamma, (double)n_step);
+  p.eta = eta;
+  return td_priority(p, S(stream));
+}
+
+int r2d2_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step,
+                   float lr, float beta1, float beta2, float eps, float grad_scale, r2d2_stream_t stream) {
+  return adam_step(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, grad_scale, S(stream));
+}
+
+// ---- replay ----
+int r2d2_replay_create(r2d2_replay_t** out, const r2d2_replay_config* cfg) {
+  return replay_create(reinterpret_cast<Replay**>(out), cfg);
+}
+int r2d2_replay_destroy(r2d2_replay_t* r) { return replay_destroy(reinterpret_cast<Replay*>(r)); }
+int r2d2_replay_add_episode(r2d2_replay_t* r, const float* obs, const float* act, const float* rew,
+                            const float* term, const float* states, int n_rows, int n_state_rows,
+                            const float* priority, int n_starts, r2d2_stream_t stream) {
+  return replay_add_episode(reinterpret_cast<Replay*>(r), obs, act, rew, term, states, n_rows, n_state_rows, priority,
+                            n_starts, S(stream));
+}
+int r2d2_replay_sample(r2d2_replay_t* r, const float* u, int batch, long long* leaf_idx, float* obs, float* act,
+                       float* rew, float* term, float* states, r2d2_stream_t stream) {
+  return replay_sample(reinterpret_cast<Replay*>(r), u, batch, leaf_idx, obs, act, rew, term, states, S(stream));
+}
+int r2d2_replay_update_priorities(r2d2_replay_t* r, const long long* leaf_idx, const float* prio, int batch,
+                                  r2d2_stream_t stream) {
+  return replay_update_priorities(reinterpret_cast<Replay*>(r), leaf_idx, prio, batch, S(stream));
+}
+int r2d2_replay_stats(r2d2_replay_t* r, r2d2_replay_stats_t* out, r2d2_stream_t stream) {
+  return replay_stats(reinterpret_cast<Replay*>(r), out, S(stream));
+}
+int r2d2_replay_decode(r2d2_replay_t* r, const long long* leaf_idx_host, int n, long long* episode_index,
+                       long long* sequence_index) {
+  return replay_decode(reinterpret_cast<Replay*>(r), leaf_idx_host, n, episode_index, sequence_index);
+}
+int r2d2_replay_tree_level(r2d2_replay_t* r, int level, const float** dev_ptr, long long* n) {
+  return replay_tree_level(reinterpret_cast<Replay*>(r), level, dev_ptr, n);
+}
+
+// ---- learner ----
+int r2d2_learner_create(r2d2_learner_t** out, const r2d2_learner_config* cfg) {
+  return learner_create(reinterpret_cast<Learner**>(out), cfg);
+}
+int r2d2_learner_destroy(r2d2_learner_t* l) { return learner_destroy(reinterpret_cast<Learner*>(l)); }
+int r2d2_learner_buffers_get(r2d2_learner_t* lh, r2d2_learner_buffers* o) {
+  R2D2_REQUIRE(lh && o, "null");
+  Learner* l = reinterpret_cast<Learner*>(lh);
+  o->obs = l->obs; o->act = l->act; o->rew = l->rew; o->term = l->term; o->states = l->states;
+  o->leaf_idx = l->leaf_idx; o->uniforms = l->uniforms; o->q_value = l->q; o->target_q_value = l->target;
+  o->td_sq = l->td_sq; o->priority = l->priority; o->losses = l->losses;
+  return R2D2_OK;
+}
+int r2d2_learner_critic_phase(r2d2_learner_t* l, r2d2_stream_t stream) {
+  R2D2_REQUIRE(l, "null");
+  return learner_critic_phase(reinterpret_cast<Learner*>(l), S(stream));
+}
+int r2d2_learner_actor_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t stream) {
+  R2D2_REQUIRE(l, "null");
+  return learner_actor_phase(reinterpret_cast<Learner*>(l), grad_scale, S(stream));
+}
+int r2d2_learner_finish_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t stream) {
+  R2D2_REQUIRE(l, "null");
+  return learner_finish_phase(reinterpret_cast<Learner*>(l), grad_scale, S(stream));
+}
+int r2d2_learner_step_count(r2d2_learner_t* l) { return l ? reinterpret_cast<Learner*>(l)->step : -1; }
+int r2d2_learner_launches_per_iteration(r2d2_learner_t* lh) {
+  if (!lh) return -1;
+  Learner* l = reinterpret_cast<Learner*>(lh);
+  return l->launches_phase[0] + l->launches_phase[1] + l->launches_phase[2];
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+// HBM-bound pieces of the learner path: fused n-step target / value rescaling / TD loss gradient /
+// sequence priority (learner.py:107-111,135-138; utils.py:17-21), Adam (learner.py:50-53,114,128),
+// bias-gradient column sums, small reductions.
+#include "elementwise.cuh"
+
+namespace r2d2 {
+namespace {
+
+__device__ __forceinline__ float value_rescale(float x) {
+  // h(x) = sign(x) * (sqrt(|x| + 1) - 1), utils.py:20-21 (no eps*x term, no inverse anywhere)
+  const float m = sqrtf(fabsf(x) + 1.0f) - 1.0f;
+  return x > 0.f ? m : (x < 0.f ? -m : 0.f);
+}
+
+// grid: ceil(B/32) CTAs, 256 threads = 8 warps; lane -> batch column, warp -> time rows i = w, w+8, ...
+__global__ void __launch_bounds__(256) td_priority_kernel(TdPriorityParams p) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  const int L = p.L, B = p.B, A = p.A;
+  const float inv_a = 1.0f / (float)A;
+  const float grad_scale = 2.0f / ((float)L * (float)B * (float)A);
+  float run_max = -INFINITY, run_sum = 0.f, sq_total = 0.f;
+  if (b < B) {
+    for (int i = w; i < L; i += 8) {
+      const float r = __ldg(p.rew + (size_t)(p.burn_in + i) * B + b);
+      const float d = __ldg(p.term + (size_t)(p.burn_in + i + p.n_step - 1) * B + b);
+      const float cont = p.gamma_n * (1.0f - d);
+      const size_t base = ((size_t)i * B + b) * A;
+      float sq = 0.f;
+      for (int a = 0; a < A; ++a) {
+        const float q = __ldg(p.q + base + a);
+        const float y = value_rescale(r + cont * __ldg(p.q_next + base + a));
+        const float diff = q - y;
+        if (p.target) p.target[base + a] = y;
+        if (p.dq) p.dq[base + a] = grad_scale * diff;
+        sq += diff * diff;
+      }
+      sq_total += sq;
+      const float td = sq * inv_a;
+      if (p.td_sq) p.td_sq[(size_t)i * B + b] = td;
+      // learner.py:137 `average_td_loss[b:-1:B]` drops flat index L*B-1, i.e. (i=L-1, b=B-1)
+      if (!(i == L - 1 && b == B - 1)) { run_max = fmaxf(run_max, td); run_sum += td; }
+    }
+  }
+  __shared__ float s_max[8][32], s_sum[8][32], s_sq[8];
+  s_max[w][lane] = run_max;
+  s_sum[w][lane] = run_sum;
+  const float wsq = warp_sum(sq_total);
+  if (lane == 0) s_sq[w] = wsq;
+  __syncthreads();
+  if (w == 0) {
+    float mx = s_max[0][lane], sm = s_sum[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { mx = fmaxf(mx, s_max[k][lane]); sm += s_sum[k][lane]; }
+    if (b < B && p.priority) {
+      const int count = L - ((b == B - 1) ? 1 : 0);
+      p.priority[b] = p.eta * mx + (1.0f - p.eta) * (sm / (float)count);  // utils.py:17-18
+    }
+    if (lane == 0 && p.loss_sum) {
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += s_sq[k];
+      atomicAdd(p.loss_sum, tot / ((float)L * (float)B * (float)A));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long ld, int M, int N,
+                                                     int rows_per_block, float* __restrict__ out, float* __restrict__ out2) {
+  // block = 32 columns x 8 row lanes; grid.x over column chunks, grid.y over row ranges; atomics into out
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc = 0.f;
+  if (col < N)
+    for (int r = r0 + w; r < r1; r += 8) acc += __ldg(x + (size_t)r * ld + col);
+  __shared__ float sm[8][32];
+  sm[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][lane];
+    atomicAdd(out + col, t);
+    if (out2) atomicAdd(out2 + col, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, const float* __restrict__ grad,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n,
+                                                   float grad_scale, float beta1, float beta2, float step_size,
+                                                   float inv_bc2_sqrt, float eps) {
+  // torch.optim.Adam single-tensor math (learner.py:50,52 defaults): lerp m, addcmul v, sqrt/bc2 + eps, addcdiv
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = grad[i] * grad_scale;
+    const float mi = m[i] + (g - m[i]) * (1.0f - beta1);
+    const float vi = v[i] * beta2 + (1.0f - beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    param[i] = param[i] - step_size * (mi / denom);
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ x, long long n, float value) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = value;
+}
+
+__global__ void __launch_bounds__(256) scaled_sum_kernel(const float* __restrict__ x, long long n, float scale,
+                                                         float* __restrict__ out) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += x[i];
+  acc = warp_sum(acc);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += sm[k];
+    atomicAdd(out, t * scale);
+  }
+}
+
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+__global__ void mul_dtanh_kernel(const float* __restrict__ d_out, const float* __restrict__ out,
+                                 float* __restrict__ d_pre, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d_pre[i] = d_out[i] * (1.0f - out[i] * out[i]);
+}
+
+}  // namespace
+
+int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t stream) {
+  add_vec_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(a, b, out, n);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int mul_dtanh(const float* d_out, const float* out, float* d_pre, long long n, cudaStream_t stream) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  mul_dtanh_kernel<<<blocks, 256, 0, stream>>>(d_out, out, d_pre, n);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int td_priority(const TdPriorityParams& p, cudaStream_t stream) {
+  R2D2_REQUIRE(p.q && p.q_next && p.rew && p.term, "null input");
+  R2D2_REQUIRE(p.L > 0 && p.B > 0 && p.A > 0, "shape");
+  if (p.loss_sum) R2D2_CUDA_TRY(cudaMemsetAsync(p.loss_sum, 0, sizeof(float), stream));
+  td_priority_kernel<<<ceil_div(p.B, 32), 256, 0, stream>>>(p);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int colsum(const float* x, long long ld, int M, int N, float* out, float* out2, cudaStream_t stream) {
+  R2D2_REQUIRE(x && out && M > 0 && N > 0, "colsum args");
+  const int col_blocks = ceil_div(N, 32);
+  int row_blocks = ceil_div(4 * 148, col_blocks);
+  if (row_blocks > ceil_div(M, 64)) row_blocks = ceil_div(M, 64);
+  if (row_blocks < 1) row_blocks = 1;
+  const int rows_per_block = ceil_div(M, row_blocks);
+  colsum_kernel<<<dim3(col_blocks, ceil_div(M, rows_per_block)), 256, 0, stream>>>(x, ld, M, N, rows_per_block, out, out2);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int adam_step(float* param, const float* grad, float* m, float* v, long long n, int step, float lr, float beta1,
+              float beta2, float eps, float grad_scale, cudaStream_t stream) {
+  R2D2_REQUIRE(param && grad && m && v && n > 0 && step >= 1, "adam args");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<blocks, 256, 0, stream>>>(param, grad, m, v, n, grad_scale, beta1, beta2, step_size, inv_bc2_sqrt, eps);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int fill_f32(float* x, long long n, float value, cudaStream_t stream) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fill_kernel<<<blocks, 256, 0, stream>>>(x, n, value);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int scaled_sum(const float* x, long long n, float scale, float* out, cudaStream_t stream) {
+  R2D2_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  scaled_sum_kernel<<<blocks, 256, 0, stream>>>(x, n, scale, out);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+}  // namespace r2d2

@@ -1,0 +1,41 @@
+// General fp32-in / fp32-out GEMM on tensor cores with bf16 hi/lo operand split (3 MMA passes,
+// fp32 accumulate) - the dense contractions of the learner path that are NOT on the serial chain:
+//   x*W1^T, z*W_ih^T, heads (models.py:33,37-39,76,80-82) and their dgrad / wgrad twins.
+#pragma once
+#include "common.cuh"
+
+namespace r2d2 {
+
+enum GemmLayout : int {
+  GEMM_NT = 0,  // A[M,K] row-major, B[N,K] row-major : C = A * B^T   (forward linear, weights [out,in])
+  GEMM_NN = 1,  // A[M,K] row-major, B[K,N] row-major : C = A * B     (dgrad: dY[M,out] * W[out,in])
+  GEMM_TN = 2   // A[K,M] row-major, B[K,N] row-major : C = A^T * B   (wgrad: dY^T * X, K = T*B rows)
+};
+
+enum GemmEpilogue : int {
+  EPI_NONE = 0,
+  EPI_TANH = 1,        // C = tanh(acc + bias)
+  EPI_MUL_DTANH = 2,   // C = (acc + bias) * (1 - Z^2)
+  EPI_ADD_Z = 3        // C = acc + bias + Z
+};
+
+struct GemmParams {
+  const float* A = nullptr;  long long lda = 0;
+  const float* B = nullptr;  long long ldb = 0;
+  // optional second K segment (GEMM_NT only): C += A2[M,K2] * B2[N,K2]^T  (critic input = cat(obs, act))
+  const float* A2 = nullptr; long long lda2 = 0;
+  const float* B2 = nullptr; long long ldb2 = 0;
+  int K2 = 0;
+  float* C = nullptr;        long long ldc = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;          // [N]
+  const float* Z = nullptr;  long long ldz = 0;   // [M,N] aux for the epilogue
+  int epilogue = EPI_NONE;
+  int split_k = 1;           // >1: partial products are atomically added into C (C must be pre-zeroed)
+};
+
+int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream);
+// picks a split-K factor so that a skinny-output wgrad GEMM fills the 148 SMs
+int gemm_suggest_split_k(int M, int N, int K);
+
+}  // namespace r2d2

@@ -1,0 +1,167 @@
+// Learner iteration engine: learner.py:84-139 (sample excluded - see replay.cu) as three phases so a
+// data-parallel caller can all-reduce the flat gradient buffers between them (NCCL lives in the host code).
+//
+//   phase 1  target_actor chain  -> target_critic chain -> online critic chain -> fused TD/priority
+//            kernel -> critic BPTT                                          (learner.py:86-113)
+//   phase 2  critic Adam; actor chain from the zero state with two cell steps per row; critic on the
+//            actor's actions with the post-step weights; dgrad through the critic; actor BPTT
+//                                                                             (learner.py:114-127)
+//   phase 3  actor Adam; hard target update every `target_update_interval` steps (learner.py:128-132)
+//
+// The actor burn-in of learner.py:92 is skipped: its state is discarded at learner.py:117 before any use.
+#include "learner.cuh"
+
+#include <cmath>
+
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "lstm_scan.cuh"
+
+namespace r2d2 {
+
+static size_t align64(size_t n) { return (n + 63) & ~(size_t)63; }
+
+int learner_create(Learner** out, const r2d2_learner_config* cfg) {
+  R2D2_REQUIRE(out && cfg, "null");
+  R2D2_REQUIRE(cfg->obs_size > 0 && cfg->n_actions > 0 && cfg->hidden > 0 && cfg->hidden % 4 == 0, "sizes");
+  R2D2_REQUIRE(cfg->batch > 0 && cfg->burn_in >= 0 && cfg->learning > 0 && cfg->n_step > 0, "window");
+  R2D2_REQUIRE(cfg->actor_params && cfg->critic_params && cfg->target_actor_params && cfg->target_critic_params,
+               "parameter buffers");
+  R2D2_REQUIRE(cfg->actor_grads && cfg->critic_grads && cfg->actor_exp_avg && cfg->actor_exp_avg_sq &&
+                   cfg->critic_exp_avg && cfg->critic_exp_avg_sq, "gradient / Adam buffers");
+  Learner* l = new Learner();
+  l->cfg = *cfg;
+  l->actor_sh = NetShape{cfg->obs_size, cfg->n_actions, cfg->hidden, false};
+  l->critic_sh = NetShape{cfg->obs_size, cfg->n_actions, cfg->hidden, true};
+  const int B = cfg->batch, Bn = cfg->burn_in, L = cfg->learning, n = cfg->n_step;
+  const int O = cfg->obs_size, A = cfg->n_actions, H = cfg->hidden;
+  const int Tt = Bn + n + L, Tc = Bn + L, Tw = Bn + L + n;
+  l->rows = Tw;
+  // one allocation, carved
+  size_t total = 0;
+  const size_t n_obs = align64((size_t)Tw * B * O), n_act = align64((size_t)Tw * B * A), n_rt = align64((size_t)Tw * B);
+  const size_t n_states = align64((size_t)8 * B * H), n_lba = align64((size_t)L * B * A);
+  const size_t n_acttc = align64((size_t)Tt * B * A);
+  total += n_obs + n_act + 2 * n_rt + n_states + align64(B) /*uniforms*/ + align64(2 * (size_t)B) /*leaf idx (int64)*/;
+  total += n_acttc + 8 * n_lba + align64((size_t)L * B) + align64(B) + 64;
+  const size_t ws_ta = ChainWs::floats(l->actor_sh, Tt, B, 1), ws_tc = ChainWs::floats(l->critic_sh, Tt, B, 1);
+  const size_t ws_c1 = ChainWs::floats(l->critic_sh, Tc, B, 1), ws_a1 = ChainWs::floats(l->actor_sh, L, B, 2);
+  const size_t ws_c2 = ChainWs::floats(l->critic_sh, L, B, 1);
+  total += ws_ta + ws_tc + ws_c1 + ws_a1 + ws_c2;
+  R2D2_CUDA_TRY(cudaMalloc(&l->arena, total * sizeof(float)));
+  R2D2_CUDA_TRY(cudaMemset(l->arena, 0, total * sizeof(float)));
+  l->arena_floats = total;
+  float* p = l->arena;
+  auto take = [&](size_t nfl) { float* r = p; p += align64(nfl); return r; };
+  l->obs = take(n_obs); l->act = take(n_act); l->rew = take(n_rt); l->term = take(n_rt);
+  l->states = take(n_states); l->uniforms = take(B);
+  l->leaf_idx = reinterpret_cast<long long*>(take(2 * (size_t)B));
+  l->act_tc = take(n_acttc);
+  l->q = take(n_lba); l->q_next = take(n_lba); l->target = take(n_lba); l->dq = take(n_lba);
+  l->mu = take(n_lba); l->q_pi = take(n_lba); l->dq_pi = take(n_lba); l->dpre_actor = take(n_lba);
+  l->td_sq = take((size_t)L * B); l->priority = take(B); l->losses = take(64);
+  l->ws_ta = ChainWs::carve(take(ws_ta), l->actor_sh, Tt, B, 1);
+  l->ws_tc = ChainWs::carve(take(ws_tc), l->critic_sh, Tt, B, 1);
+  l->ws_c1 = ChainWs::carve(take(ws_c1), l->critic_sh, Tc, B, 1);
+  l->ws_a1 = ChainWs::carve(take(ws_a1), l->actor_sh, L, B, 2);
+  l->ws_c2 = ChainWs::carve(take(ws_c2), l->critic_sh, L, B, 1);
+  *out = l;
+  return R2D2_OK;
+}
+
+int learner_destroy(Learner* l) {
+  if (!l) return R2D2_OK;
+  cudaFree(l->arena);
+  delete l;
+  return R2D2_OK;
+}
+
+int learner_critic_phase(Learner* l, cudaStream_t st) {
+  const r2d2_learner_config& c = l->cfg;
+  const int B = c.batch, Bn = c.burn_in, L = c.learning, n = c.n_step, A = c.n_actions, H = c.hidden;
+  const int Tt = Bn + n + L, Tc = Bn + L;
+  const long long launches0 = launch_count();
+  const NetParams Pa_t = NetParams::from_flat(c.target_actor_params, l->actor_sh);
+  const NetParams Pc_t = NetParams::from_flat(c.target_critic_params, l->critic_sh);
+  const NetParams Pc = NetParams::from_flat(c.critic_params, l->critic_sh);
+  const NetParams Gc = NetParams::from_flat(c.critic_grads, l->critic_sh);
+  const size_t BH = (size_t)B * H;
+  const float* st_ta = l->states + 2 * BH;   // states[1] = target_actor (hx, cx)
+  const float* st_c = l->states + 4 * BH;    // states[2] = critic
+  const float* st_tc = l->states + 6 * BH;   // states[3] = target_critic
+
+  // target actor over rows [0, Bn+n+L) from its stored state (learner.py:87,94,106); actions for the last L rows
+  R2D2_TRY(net_forward(l->actor_sh, Pa_t, l->ws_ta, l->obs, nullptr, st_ta, st_ta + BH, Tt, B, 1, st));
+  R2D2_CUDA_TRY(cudaMemcpyAsync(l->act_tc, l->act, sizeof(float) * (size_t)(Bn + n) * B * A,
+                                cudaMemcpyDeviceToDevice, st));
+  R2D2_TRY(net_head_forward(l->actor_sh, Pa_t, l->ws_ta, Bn + n, Tt, B, 1, l->act_tc + (size_t)(Bn + n) * B * A, A, st));
+  // target critic: stored actions while burning in, target-actor actions afterwards (learner.py:95,106)
+  R2D2_TRY(net_forward(l->critic_sh, Pc_t, l->ws_tc, l->obs, l->act_tc, st_tc, st_tc + BH, Tt, B, 1, st));
+  R2D2_TRY(net_head_forward(l->critic_sh, Pc_t, l->ws_tc, Bn + n, Tt, B, 1, l->q_next, A, st));
+  // online critic over rows [0, Bn+L) with stored actions (learner.py:93,105); burn-in stays on the tape (Q4)
+  R2D2_TRY(net_forward(l->critic_sh, Pc, l->ws_c1, l->obs, l->act, st_c, st_c + BH, Tc, B, 1, st));
+  R2D2_TRY(net_head_forward(l->critic_sh, Pc, l->ws_c1, Bn, Tc, B, 1, l->q, A, st));
+
+  TdPriorityParams tp;
+  tp.q = l->q; tp.q_next = l->q_next; tp.rew = l->rew; tp.term = l->term;
+  tp.target = l->target; tp.dq = l->dq; tp.td_sq = l->td_sq; tp.priority = l->priority; tp.loss_sum = l->losses;
+  tp.L = L; tp.B = B; tp.A = A; tp.burn_in = Bn; tp.n_step = n;
+  tp.gamma_n = (float)std::pow((double)c.gamma, (double)n);
+  tp.eta = c.eta;
+  R2D2_TRY(td_priority(tp, st));
+
+  R2D2_CUDA_TRY(cudaMemsetAsync(c.critic_grads, 0, sizeof(float) * l->critic_sh.param_count(), st));
+  R2D2_TRY(net_backward(l->critic_sh, Pc, &Gc, l->ws_c1, l->obs, l->act, l->dq, Bn, Tc, B, 1, nullptr, nullptr, st));
+  l->launches_phase[0] = (int)(launch_count() - launches0);
+  return R2D2_OK;
+}
+
+int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t st) {
+  const r2d2_learner_config& c = l->cfg;
+  const int B = c.batch, Bn = c.burn_in, L = c.learning, A = c.n_actions, O = c.obs_size;
+  const long long launches0 = launch_count();
+  const NetParams Pa = NetParams::from_flat(c.actor_params, l->actor_sh);
+  const NetParams Ga = NetParams::from_flat(c.actor_grads, l->actor_sh);
+  const NetParams Pc = NetParams::from_flat(c.critic_params, l->critic_sh);
+  const long long LBA = (long long)L * B * A;
+
+  R2D2_TRY(adam_step(c.critic_params, c.critic_grads, c.critic_exp_avg, c.critic_exp_avg_sq,
+                     (long long)l->critic_sh.param_count(), l->step + 1, c.critic_lr, 0.9f, 0.999f, 1e-8f,
+                     grad_scale, st));                                                     // learner.py:114
+
+  const float* obs_l = l->obs + (size_t)Bn * B * O;  // rows [Bn, Bn+L)
+  // actor from the zero state, LSTM stepped twice per row (learner.py:117,122-123); mu = output of the 2nd call
+  R2D2_TRY(net_forward(l->actor_sh, Pa, l->ws_a1, obs_l, nullptr, nullptr, nullptr, L, B, 2, st));
+  R2D2_TRY(net_head_forward(l->actor_sh, Pa, l->ws_a1, 0, L, B, 2, l->mu, A, st));
+  // critic (post-Adam weights, zero state) on the actor's actions; loss = mean(-Q) (learner.py:118,123-124)
+  R2D2_TRY(net_forward(l->critic_sh, Pc, l->ws_c2, obs_l, l->mu, nullptr, nullptr, L, B, 1, st));
+  R2D2_TRY(net_head_forward(l->critic_sh, Pc, l->ws_c2, 0, L, B, 1, l->q_pi, A, st));
+  R2D2_TRY(scaled_sum(l->q_pi, LBA, -1.0f / (float)LBA, l->losses + 1, st));
+  R2D2_TRY(fill_f32(l->dq_pi, LBA, -1.0f / (float)LBA, st));
+  // dgrad only through the critic (its weight grads are wasted work in the reference); d_pre(actor) = dQ/da * (1-mu^2)
+  R2D2_TRY(net_backward(l->critic_sh, Pc, nullptr, l->ws_c2, obs_l, l->mu, l->dq_pi, 0, L, B, 1, l->dpre_actor,
+                        l->mu, st));
+  R2D2_CUDA_TRY(cudaMemsetAsync(c.actor_grads, 0, sizeof(float) * l->actor_sh.param_count(), st));
+  R2D2_TRY(net_backward(l->actor_sh, Pa, &Ga, l->ws_a1, obs_l, nullptr, l->dpre_actor, 0, L, B, 2, nullptr, nullptr, st));
+  l->launches_phase[1] = (int)(launch_count() - launches0);
+  return R2D2_OK;
+}
+
+int learner_finish_phase(Learner* l, float grad_scale, cudaStream_t st) {
+  const r2d2_learner_config& c = l->cfg;
+  const long long launches0 = launch_count();
+  R2D2_TRY(adam_step(c.actor_params, c.actor_grads, c.actor_exp_avg, c.actor_exp_avg_sq,
+                     (long long)l->actor_sh.param_count(), l->step + 1, c.actor_lr, 0.9f, 0.999f, 1e-8f, grad_scale,
+                     st));                                                                 // learner.py:128
+  l->step += 1;
+  if (c.target_update_interval > 0 && l->step % c.target_update_interval == 0) {           // learner.py:131-132
+    R2D2_CUDA_TRY(cudaMemcpyAsync(c.target_actor_params, c.actor_params, sizeof(float) * l->actor_sh.param_count(),
+                                  cudaMemcpyDeviceToDevice, st));
+    R2D2_CUDA_TRY(cudaMemcpyAsync(c.target_critic_params, c.critic_params, sizeof(float) * l->critic_sh.param_count(),
+                                  cudaMemcpyDeviceToDevice, st));
+  }
+  l->launches_phase[2] = (int)(launch_count() - launches0);
+  return R2D2_OK;
+}
+
+}  // namespace r2d2

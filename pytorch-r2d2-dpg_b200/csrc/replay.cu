@@ -1,0 +1,347 @@
+// GPU-resident prioritized sequence replay shard (replaces LearnerReplayMemory, replay_memory.py:67-175).
+//
+// HBM layout (SoA, one "row" per stored env step incl. the n_step pad rows of actor.py:173):
+//   obs_rows [cap,O]  act_rows [cap,A]  rew_rows [cap]  term_rows [cap]  state_rows [cap,4,2,H]
+// Episodes occupy contiguous row ranges of a ring; FIFO eviction (replay_memory.py:148-152).
+// Sum tree: one leaf per ROW (priority 0 for rows that are not valid sequence starts), fan-out 32:
+// every node is the left-to-right fp32 sum of its 32 children (one 128-byte line), so the tree has
+// ceil(log32(cap)) levels (5 for 2M rows) instead of 21 dependent loads of a binary tree, and the
+// CUDA tree and its C restatement (oracle/sumtree_oracle.c) are bit-identical by construction.
+#include <deque>
+#include <map>
+#include <vector>
+
+#include "replay.cuh"
+
+namespace r2d2 {
+
+namespace {
+
+__global__ void __launch_bounds__(256) tree_sample_kernel(TreeView tv, const float* __restrict__ u, int batch,
+                                                          long long* __restrict__ leaf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const int top = tv.levels - 1;
+  const float total = tv.lvl[top][0];
+  float r = __fmul_rn(u[i], total);
+  long long idx = 0;
+  for (int l = top; l >= 1; --l) {
+    const float4* ch4 = reinterpret_cast<const float4*>(tv.lvl[l - 1] + idx * TREE_K);
+    float c[TREE_K];
+#pragma unroll
+    for (int k = 0; k < TREE_K / 4; ++k) {
+      const float4 v = ch4[k];
+      c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w;
+    }
+    int pick = -1;
+#pragma unroll
+    for (int k = 0; k < TREE_K; ++k) {
+      if (pick < 0) {
+        if (r < c[k]) pick = k;
+        else r = __fsub_rn(r, c[k]);
+      }
+    }
+    if (pick < 0) {  // rounding pushed the residual past the last child: take the last non-empty child
+      float cl = 0.f;
+#pragma unroll
+      for (int k = 0; k < TREE_K; ++k)
+        if (c[k] > 0.f) { pick = k; cl = c[k]; }
+      if (pick < 0) pick = 0;
+      r = __fmul_rn(cl, 0.99999994f);
+    }
+    idx = idx * TREE_K + pick;
+  }
+  leaf[i] = idx;
+}
+
+__device__ __forceinline__ float node_sum(const float* __restrict__ children) {
+  const float4* ch4 = reinterpret_cast<const float4*>(children);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < TREE_K / 4; ++k) {
+    const float4 v = ch4[k];
+    s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
+  }
+  return s;
+}
+
+// single CTA: write the batch's leaves (highest batch index wins on duplicates, learner.py:136-139
+// executes the writes in batch order), then refresh every ancestor level by level.
+__global__ void __launch_bounds__(1024) tree_update_kernel(TreeView tv, const long long* __restrict__ leaf,
+                                                           const float* __restrict__ prio, int batch) {
+  for (int i = threadIdx.x; i < batch; i += blockDim.x) {
+    const long long li = leaf[i];
+    bool winner = true;
+    for (int j = i + 1; j < batch; ++j)
+      if (leaf[j] == li) { winner = false; break; }
+    if (winner) tv.lvl[0][li] = prio[i];
+  }
+  __syncthreads();
+  long long div = TREE_K;
+  for (int l = 1; l < tv.levels; ++l) {
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) {
+      const long long node = leaf[i] / div;
+      tv.lvl[l][node] = node_sum(tv.lvl[l - 1] + node * TREE_K);
+    }
+    __syncthreads();
+    div *= TREE_K;
+  }
+}
+
+__global__ void __launch_bounds__(256) tree_recompute_range_kernel(TreeView tv, int level, long long first,
+                                                                   long long count) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const long long node = first + i;
+  tv.lvl[level][node] = node_sum(tv.lvl[level - 1] + node * TREE_K);
+}
+
+// out[t][b][w] = rows[(leaf[b] + t) * W + w]
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ rows, int W,
+                                                          const long long* __restrict__ leaf, int T, int B,
+                                                          float* __restrict__ out) {
+  const long long total = (long long)T * B * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long tb = i / W;
+    const int b = (int)(tb % B);
+    const int t = (int)(tb / B);
+    out[i] = __ldg(rows + (leaf[b] + t) * W + w);
+  }
+}
+
+// out[nh][b][h] = state_rows[leaf[b]][nh][h], nh = net*2 + (hx|cx)
+__global__ void __launch_bounds__(256) gather_states_kernel(const float* __restrict__ state_rows, int H,
+                                                            const long long* __restrict__ leaf, int B,
+                                                            float* __restrict__ out) {
+  const long long total = (long long)8 * B * H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(i % H);
+    const long long nb = i / H;
+    const int b = (int)(nb % B);
+    const int nh = (int)(nb / B);
+    out[i] = __ldg(state_rows + (leaf[b] * 8 + nh) * H + h);
+  }
+}
+
+int grid_for(long long total) {
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+struct Episode {
+  long long row_start;
+  int n_rows;
+  int n_starts;
+  long long serial;
+};
+
+struct Replay {
+  r2d2_replay_config cfg;
+  int rows_per_window;
+  float *obs_rows = nullptr, *act_rows = nullptr, *rew_rows = nullptr, *term_rows = nullptr, *state_rows = nullptr;
+  std::vector<float*> level_alloc;
+  TreeView tv;
+  std::deque<Episode> episodes;
+  std::map<long long, long long> by_row;  // row_start -> serial
+  long long next_serial = 0;
+  long long head = 0;
+  long long sequence_counter = 0;
+  long long rows_used = 0;
+};
+
+static int recompute_ancestors(Replay* r, long long first_leaf, long long n_leaves, cudaStream_t stream) {
+  long long lo = first_leaf, hi = first_leaf + n_leaves - 1;
+  for (int l = 1; l < r->tv.levels; ++l) {
+    lo /= TREE_K;
+    hi /= TREE_K;
+    const long long count = hi - lo + 1;
+    tree_recompute_range_kernel<<<(int)((count + 255) / 256), 256, 0, stream>>>(r->tv, l, lo, count);
+    count_launch();
+  }
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int replay_create(Replay** out, const r2d2_replay_config* cfg) {
+  R2D2_REQUIRE(out && cfg, "null");
+  R2D2_REQUIRE(cfg->obs_size > 0 && cfg->n_actions > 0 && cfg->hidden > 0, "sizes");
+  R2D2_REQUIRE(cfg->capacity_rows > 0, "capacity_rows");
+  Replay* r = new Replay();
+  r->cfg = *cfg;
+  r->rows_per_window = cfg->burn_in + cfg->learning + cfg->n_step;
+  const long long cap = cfg->capacity_rows;
+  auto dmalloc = [&](float** p, long long n) -> int {
+    R2D2_CUDA_TRY(cudaMalloc(p, sizeof(float) * (size_t)n));
+    R2D2_CUDA_TRY(cudaMemset(*p, 0, sizeof(float) * (size_t)n));
+    return R2D2_OK;
+  };
+  int rc = R2D2_OK;
+  if ((rc = dmalloc(&r->obs_rows, cap * cfg->obs_size)) || (rc = dmalloc(&r->act_rows, cap * cfg->n_actions)) ||
+      (rc = dmalloc(&r->rew_rows, cap)) || (rc = dmalloc(&r->term_rows, cap)) ||
+      (rc = dmalloc(&r->state_rows, cap * 8 * cfg->hidden))) {
+    delete r;
+    return rc;
+  }
+  // levels: n[0] = leaves, n[l+1] = ceil(n[l]/32), last level has one node (the total)
+  long long n = (cap + TREE_K - 1) / TREE_K * TREE_K;
+  int levels = 0;
+  while (true) {
+    R2D2_REQUIRE(levels < TREE_MAX_LEVELS, "tree too deep");
+    const long long parents = (n + TREE_K - 1) / TREE_K;
+    const long long alloc = (n > 1) ? parents * TREE_K : TREE_K;
+    float* p = nullptr;
+    if ((rc = dmalloc(&p, alloc))) { delete r; return rc; }
+    r->level_alloc.push_back(p);
+    r->tv.lvl[levels] = p;
+    r->tv.n[levels] = n;
+    ++levels;
+    if (n == 1) break;
+    n = parents;
+  }
+  r->tv.levels = levels;
+  *out = r;
+  return R2D2_OK;
+}
+
+int replay_destroy(Replay* r) {
+  if (!r) return R2D2_OK;
+  cudaFree(r->obs_rows); cudaFree(r->act_rows); cudaFree(r->rew_rows); cudaFree(r->term_rows); cudaFree(r->state_rows);
+  for (float* p : r->level_alloc) cudaFree(p);
+  delete r;
+  return R2D2_OK;
+}
+
+static int evict_front(Replay* r, cudaStream_t stream) {
+  const Episode e = r->episodes.front();
+  r->episodes.pop_front();
+  r->by_row.erase(e.row_start);
+  // replay_memory.py:149: the counter drops by len(episode) - sequence_length (sic: not the amount added at :147)
+  r->sequence_counter -= e.n_rows - (r->cfg.burn_in + r->cfg.learning);
+  r->rows_used -= e.n_rows;
+  if (e.n_starts > 0) {
+    R2D2_CUDA_TRY(cudaMemsetAsync(r->tv.lvl[0] + e.row_start, 0, sizeof(float) * e.n_starts, stream));
+    R2D2_TRY(recompute_ancestors(r, e.row_start, e.n_starts, stream));
+  }
+  return R2D2_OK;
+}
+
+int replay_add_episode(Replay* r, const float* obs, const float* act, const float* rew, const float* term,
+                       const float* states, int n_rows, int n_state_rows, const float* priority, int n_starts,
+                       cudaStream_t stream) {
+  R2D2_REQUIRE(r && obs && act && rew && term && states, "null");
+  R2D2_REQUIRE(n_rows >= r->rows_per_window, "episode shorter than one window");
+  R2D2_REQUIRE(n_starts >= 0 && n_starts <= n_rows - r->rows_per_window + 1, "n_starts exceeds valid window starts");
+  R2D2_REQUIRE(n_state_rows >= n_starts && n_state_rows <= n_rows, "state rows");
+  R2D2_REQUIRE(n_starts == 0 || priority, "priority");
+  R2D2_REQUIRE(n_rows <= r->cfg.capacity_rows, "episode larger than the ring");
+  const int O = r->cfg.obs_size, A = r->cfg.n_actions, H = r->cfg.hidden;
+  if (r->head + n_rows > r->cfg.capacity_rows) r->head = 0;  // wrap: the tail gap stays unused
+  const long long start = r->head, end = start + n_rows;
+  while (!r->episodes.empty()) {
+    const Episode& f = r->episodes.front();
+    const bool overlap = f.row_start < end && start < f.row_start + f.n_rows;
+    if (!overlap) break;
+    R2D2_TRY(evict_front(r, stream));
+  }
+  for (const Episode& e : r->episodes)
+    R2D2_REQUIRE(!(e.row_start < end && start < e.row_start + e.n_rows), "ring overlap with a live episode");
+  R2D2_CUDA_TRY(cudaMemcpyAsync(r->obs_rows + start * O, obs, sizeof(float) * (size_t)n_rows * O, cudaMemcpyHostToDevice, stream));
+  R2D2_CUDA_TRY(cudaMemcpyAsync(r->act_rows + start * A, act, sizeof(float) * (size_t)n_rows * A, cudaMemcpyHostToDevice, stream));
+  R2D2_CUDA_TRY(cudaMemcpyAsync(r->rew_rows + start, rew, sizeof(float) * (size_t)n_rows, cudaMemcpyHostToDevice, stream));
+  R2D2_CUDA_TRY(cudaMemcpyAsync(r->term_rows + start, term, sizeof(float) * (size_t)n_rows, cudaMemcpyHostToDevice, stream));
+  R2D2_CUDA_TRY(cudaMemcpyAsync(r->state_rows + start * 8 * H, states, sizeof(float) * (size_t)n_state_rows * 8 * H,
+                                cudaMemcpyHostToDevice, stream));
+  if (n_state_rows < n_rows)
+    R2D2_CUDA_TRY(cudaMemsetAsync(r->state_rows + (start + n_state_rows) * 8 * H, 0,
+                                  sizeof(float) * (size_t)(n_rows - n_state_rows) * 8 * H, stream));
+  if (n_starts > 0)
+    R2D2_CUDA_TRY(cudaMemcpyAsync(r->tv.lvl[0] + start, priority, sizeof(float) * (size_t)n_starts,
+                                  cudaMemcpyHostToDevice, stream));
+  if (n_rows > n_starts)
+    R2D2_CUDA_TRY(cudaMemsetAsync(r->tv.lvl[0] + start + n_starts, 0, sizeof(float) * (size_t)(n_rows - n_starts), stream));
+  R2D2_TRY(recompute_ancestors(r, start, n_rows, stream));
+  Episode e{start, n_rows, n_starts, r->next_serial++};
+  r->episodes.push_back(e);
+  r->by_row[start] = e.serial;
+  r->head = end;
+  r->rows_used += n_rows;
+  r->sequence_counter += n_rows - (r->rows_per_window - 1);  // replay_memory.py:147
+  while (r->cfg.max_sequences > 0 && r->sequence_counter > r->cfg.max_sequences && r->episodes.size() > 1)
+    R2D2_TRY(evict_front(r, stream));
+  R2D2_CUDA_TRY(cudaStreamSynchronize(stream));  // host buffers may be released by the caller
+  return R2D2_OK;
+}
+
+int replay_sample(Replay* r, const float* u, int batch, long long* leaf_idx, float* obs, float* act, float* rew,
+                  float* term, float* states, cudaStream_t stream) {
+  R2D2_REQUIRE(r && u && leaf_idx && batch > 0, "args");
+  R2D2_REQUIRE(!r->episodes.empty(), "replay is empty");
+  tree_sample_kernel<<<ceil_div(batch, 256), 256, 0, stream>>>(r->tv, u, batch, leaf_idx);
+  count_launch();
+  const int T = r->rows_per_window, O = r->cfg.obs_size, A = r->cfg.n_actions, H = r->cfg.hidden;
+  if (obs) { gather_rows_kernel<<<grid_for((long long)T * batch * O), 256, 0, stream>>>(r->obs_rows, O, leaf_idx, T, batch, obs); count_launch(); }
+  if (act) { gather_rows_kernel<<<grid_for((long long)T * batch * A), 256, 0, stream>>>(r->act_rows, A, leaf_idx, T, batch, act); count_launch(); }
+  if (rew) { gather_rows_kernel<<<grid_for((long long)T * batch), 256, 0, stream>>>(r->rew_rows, 1, leaf_idx, T, batch, rew); count_launch(); }
+  if (term) { gather_rows_kernel<<<grid_for((long long)T * batch), 256, 0, stream>>>(r->term_rows, 1, leaf_idx, T, batch, term); count_launch(); }
+  if (states) { gather_states_kernel<<<grid_for((long long)8 * batch * H), 256, 0, stream>>>(r->state_rows, H, leaf_idx, batch, states); count_launch(); }
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int replay_update_priorities(Replay* r, const long long* leaf_idx, const float* prio, int batch, cudaStream_t stream) {
+  R2D2_REQUIRE(r && leaf_idx && prio && batch > 0, "args");
+  tree_update_kernel<<<1, 1024, 0, stream>>>(r->tv, leaf_idx, prio, batch);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int replay_stats(Replay* r, r2d2_replay_stats_t* out, cudaStream_t stream) {
+  R2D2_REQUIRE(r && out, "args");
+  float total = 0.f;
+  R2D2_CUDA_TRY(cudaMemcpyAsync(&total, r->tv.lvl[r->tv.levels - 1], sizeof(float), cudaMemcpyDeviceToHost, stream));
+  R2D2_CUDA_TRY(cudaStreamSynchronize(stream));
+  out->n_episodes = (long long)r->episodes.size();
+  out->n_rows_used = r->rows_used;
+  out->sequence_counter = r->sequence_counter;
+  out->capacity_rows = r->cfg.capacity_rows;
+  out->tree_levels = r->tv.levels;
+  long long nodes = 0;
+  for (int l = 0; l < r->tv.levels; ++l) nodes += r->tv.n[l];
+  out->tree_nodes = nodes;
+  out->total_priority = total;
+  return R2D2_OK;
+}
+
+int replay_decode(Replay* r, const long long* leaf_host, int n, long long* episode_index, long long* sequence_index) {
+  R2D2_REQUIRE(r && leaf_host && episode_index && sequence_index, "args");
+  const long long front_serial = r->episodes.empty() ? 0 : r->episodes.front().serial;
+  for (int i = 0; i < n; ++i) {
+    episode_index[i] = sequence_index[i] = -1;
+    auto it = r->by_row.upper_bound(leaf_host[i]);
+    if (it == r->by_row.begin()) continue;
+    --it;
+    const Episode& e = r->episodes[(size_t)(it->second - front_serial)];
+    if (leaf_host[i] < e.row_start + e.n_rows) {
+      episode_index[i] = it->second - front_serial;
+      sequence_index[i] = leaf_host[i] - e.row_start;
+    }
+  }
+  return R2D2_OK;
+}
+
+int replay_tree_level(Replay* r, int level, const float** dev_ptr, long long* n) {
+  R2D2_REQUIRE(r && level >= 0 && level < r->tv.levels, "level");
+  *dev_ptr = r->tv.lvl[level];
+  *n = r->tv.n[level];
+  return R2D2_OK;
+}
+
+}  // namespace r2d2
