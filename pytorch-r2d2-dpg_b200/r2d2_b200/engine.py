@@ -1,0 +1,278 @@
+"""Host-side orchestration of the native learner path (torch = device memory, streams, NCCL).
+
+`LearnerEngine` owns the flat parameter / gradient / Adam buffers (torch CUDA tensors), exposes them
+as `state_dict()`-compatible views with the reference's keys (models.py:17-19), and drives the three
+native phases of one learner iteration (learner.py:84-139).  With torch.distributed initialised it
+all-reduces the two flat gradient buffers between the phases: nothing else crosses GPUs.
+
+`DeviceReplay` is the per-GPU replay shard (replaces LearnerReplayMemory storage + sampling,
+replay_memory.py:67-136) with the sum tree in HBM.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from ctypes import byref, c_longlong, c_void_p
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import native as nv
+
+PARAM_KEYS = ("l1.weight", "l1.bias", "l2.weight_ih", "l2.weight_hh", "l2.bias_ih", "l2.bias_hh",
+              "l3.weight", "l3.bias")
+
+
+@dataclass
+class PathConfig:
+    """Hyper-parameters of the path; defaults are the reference's literals (learner.py:29-34,43-49)."""
+    obs: int
+    act: int
+    hidden: int = 128
+    batch: int = 32
+    burn_in: int = 20
+    learning: int = 40
+    n_step: int = 5
+    gamma: float = 0.997
+    actor_lr: float = 1e-4
+    critic_lr: float = 1e-3
+    eta: float = 0.9
+    target_interval: int = 500
+
+    @property
+    def rows(self) -> int:
+        return self.burn_in + self.learning + self.n_step
+
+
+def param_shapes(cfg: PathConfig, critic: bool):
+    H, A = cfg.hidden, cfg.act
+    I = cfg.obs + (cfg.act if critic else 0)
+    return OrderedDict([("l1.weight", (H, I)), ("l1.bias", (H,)), ("l2.weight_ih", (4 * H, H)),
+                        ("l2.weight_hh", (4 * H, H)), ("l2.bias_ih", (4 * H,)), ("l2.bias_hh", (4 * H,)),
+                        ("l3.weight", (A, H)), ("l3.bias", (A,))])
+
+
+def flat_views(flat: torch.Tensor, cfg: PathConfig, critic: bool):
+    """state_dict-ordered views into a flat parameter block (no copies)."""
+    out, off = OrderedDict(), 0
+    for k, shp in param_shapes(cfg, critic).items():
+        n = int(np.prod(shp))
+        out[k] = flat[off:off + n].view(shp)
+        off += n
+    assert off == flat.numel()
+    return out
+
+
+def init_reference_params(cfg: PathConfig, critic: bool, generator: torch.Generator | None = None):
+    """Fresh parameters with the reference's distributions (models.py:8-11,21-25): fan-in uniform keyed
+    on out_features for l1 / LSTM weights, LSTMCell-default U(+-1/sqrt(H)) biases, Linear-default l1 bias,
+    l3 U(+-3e-3) / 3e-4.  (Seed-for-seed identity with torch's module constructors is not needed here;
+    parity tests load the reference's own tensors.)"""
+    H = cfg.hidden
+    shapes = param_shapes(cfg, critic)
+    u = lambda shp, b: (torch.rand(shp, generator=generator) * 2 - 1) * b  # noqa: E731
+    I = shapes["l1.weight"][1]
+    p = OrderedDict()
+    p["l1.weight"] = u(shapes["l1.weight"], 1.0 / np.sqrt(H))
+    p["l1.bias"] = u(shapes["l1.bias"], 1.0 / np.sqrt(I))
+    p["l2.weight_ih"] = u(shapes["l2.weight_ih"], 1.0 / np.sqrt(4 * H))
+    p["l2.weight_hh"] = u(shapes["l2.weight_hh"], 1.0 / np.sqrt(4 * H))
+    p["l2.bias_ih"] = u(shapes["l2.bias_ih"], 1.0 / np.sqrt(H))
+    p["l2.bias_hh"] = u(shapes["l2.bias_hh"], 1.0 / np.sqrt(H))
+    p["l3.weight"] = u(shapes["l3.weight"], 3e-3)
+    p["l3.bias"] = torch.full(shapes["l3.bias"], 3e-4)
+    return p
+
+
+class LearnerEngine:
+    def __init__(self, cfg: PathConfig, device=None, seed: int = 1):
+        if not torch.cuda.is_available():
+            raise nv.NativeError("LearnerEngine needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = nv.lib()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+        na = sum(int(np.prod(s)) for s in param_shapes(cfg, False).values())
+        nc = sum(int(np.prod(s)) for s in param_shapes(cfg, True).values())
+        z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)  # noqa: E731
+        self.flat = {"actor": z(na), "critic": z(nc), "target_actor": z(na), "target_critic": z(nc)}
+        self.grads = {"actor": z(na), "critic": z(nc)}
+        self.exp_avg = {"actor": z(na), "critic": z(nc)}
+        self.exp_avg_sq = {"actor": z(na), "critic": z(nc)}
+        g = torch.Generator().manual_seed(seed)
+        self.load_state_dicts(init_reference_params(cfg, False, g), init_reference_params(cfg, True, g))
+        c = nv.LearnerConfig(cfg.obs, cfg.act, cfg.hidden, cfg.batch, cfg.burn_in, cfg.learning, cfg.n_step,
+                             cfg.gamma, cfg.actor_lr, cfg.critic_lr, cfg.eta, cfg.target_interval,
+                             self.flat["actor"].data_ptr(), self.flat["critic"].data_ptr(),
+                             self.flat["target_actor"].data_ptr(), self.flat["target_critic"].data_ptr(),
+                             self.grads["actor"].data_ptr(), self.grads["critic"].data_ptr(),
+                             self.exp_avg["actor"].data_ptr(), self.exp_avg_sq["actor"].data_ptr(),
+                             self.exp_avg["critic"].data_ptr(), self.exp_avg_sq["critic"].data_ptr())
+        self._h = c_void_p()
+        nv.check(self.lib.r2d2_learner_create(byref(self._h), byref(c)))
+        b = nv.LearnerBuffers()
+        nv.check(self.lib.r2d2_learner_buffers_get(self._h, byref(b)))
+        T, B, O, A, H, L = cfg.rows, cfg.batch, cfg.obs, cfg.act, cfg.hidden, cfg.learning
+        dev = self.device
+        self.obs = nv.view_f32(b.obs, (T, B, O), dev)
+        self.act = nv.view_f32(b.act, (T, B, A), dev)
+        self.rew = nv.view_f32(b.rew, (T, B), dev)
+        self.term = nv.view_f32(b.term, (T, B), dev)
+        self.states = nv.view_f32(b.states, (4, 2, B, H), dev)
+        self.leaf_idx = nv.view_i64(b.leaf_idx, (B,), dev)
+        self.uniforms = nv.view_f32(b.uniforms, (B,), dev)
+        self.q_value = nv.view_f32(b.q_value, (L * B, A), dev)
+        self.target_q_value = nv.view_f32(b.target_q_value, (L * B, A), dev)
+        self.td_sq = nv.view_f32(b.td_sq, (L * B,), dev)
+        self.priority = nv.view_f32(b.priority, (B,), dev)
+        self.losses = nv.view_f32(b.losses, (2,), dev)
+        self.world = 1
+        self._dist = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.r2d2_learner_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters -------------------------------------------------------------------------
+    def views(self, net: str, what: str = "params"):
+        src = {"params": self.flat, "grads": self.grads, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}[what]
+        return flat_views(src[net], self.cfg, "critic" in net)
+
+    def state_dict(self, net: str):
+        return OrderedDict((k, v.detach().clone()) for k, v in self.views(net).items())
+
+    def load_state_dicts(self, actor, critic, target_actor=None, target_critic=None):
+        def put(net, sd):
+            for k, v in self.views(net).items():
+                v.copy_(torch.as_tensor(np.asarray(sd[k]) if not isinstance(sd[k], torch.Tensor) else sd[k],
+                                        dtype=torch.float32).to(self.device))
+        put("actor", actor)
+        put("critic", critic)
+        put("target_actor", target_actor if target_actor is not None else actor)
+        put("target_critic", target_critic if target_critic is not None else critic)
+
+    def enable_data_parallel(self):
+        """Gradients are averaged over ranks at the two optimiser steps (NCCL all-reduce of the flat buffers)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self._dist = dist
+            self.world = dist.get_world_size()
+            for net in ("actor", "critic", "target_actor", "target_critic"):
+                dist.broadcast(self.flat[net], src=0)
+
+    # ---- batch ------------------------------------------------------------------------------
+    def set_batch(self, batch: dict):
+        """Copy an already sampled time-major batch (replay_memory.py:123-136 layout) into the engine."""
+        cv = lambda x: torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x,  # noqa: E731
+                                       dtype=torch.float32).to(self.device, non_blocking=True)
+        self.obs.copy_(cv(batch["obs"]))
+        self.act.copy_(cv(batch["act"]))
+        self.rew.copy_(cv(batch["rew"]).reshape(self.rew.shape))
+        self.term.copy_(cv(batch["term"]).reshape(self.term.shape))
+        for i, k in enumerate(("a_state", "ta_state", "c_state", "tc_state")):
+            self.states[i].copy_(cv(batch[k]))
+
+    # ---- one learner iteration (learner.py:86-132) on the batch currently in the engine ------------
+    def step(self):
+        s = nv.current_stream()
+        scale = 1.0 / self.world
+        nv.check(self.lib.r2d2_learner_critic_phase(self._h, s))
+        if self._dist is not None:
+            self._dist.all_reduce(self.grads["critic"])
+        nv.check(self.lib.r2d2_learner_actor_phase(self._h, scale, s))
+        if self._dist is not None:
+            self._dist.all_reduce(self.grads["actor"])
+        nv.check(self.lib.r2d2_learner_finish_phase(self._h, scale, s))
+
+    @property
+    def step_count(self) -> int:
+        return int(self.lib.r2d2_learner_step_count(self._h))
+
+    @property
+    def launches_per_iteration(self) -> int:
+        return int(self.lib.r2d2_learner_launches_per_iteration(self._h))
+
+
+class DeviceReplay:
+    """One replay shard in HBM with a 32-ary sum tree (one leaf per stored row)."""
+
+    def __init__(self, cfg: PathConfig, capacity_rows: int, max_sequences: int = 0, device=None):
+        if not torch.cuda.is_available():
+            raise nv.NativeError("DeviceReplay needs a CUDA device; there is no CPU fallback")
+        self.lib = nv.lib()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+        rc = nv.ReplayConfig(cfg.obs, cfg.act, cfg.hidden, cfg.burn_in, cfg.learning, cfg.n_step,
+                             int(capacity_rows), int(max_sequences))
+        self._h = c_void_p()
+        nv.check(self.lib.r2d2_replay_create(byref(self._h), byref(rc)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.r2d2_replay_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_episode(self, obs, act, rew, term, states, priority):
+        """obs [n_rows,O], act [n_rows,A], rew/term [n_rows], states [n_real,4,2,H], priority [n_starts] (host)."""
+        obs, po = nv.host_f32(obs)
+        act, pa = nv.host_f32(act)
+        rew, pr = nv.host_f32(np.asarray(rew).reshape(-1))
+        term, pt = nv.host_f32(np.asarray(term).reshape(-1))
+        states, ps = nv.host_f32(states)
+        priority, pp = nv.host_f32(np.asarray(priority).reshape(-1))
+        nv.check(self.lib.r2d2_replay_add_episode(self._h, po, pa, pr, pt, ps, obs.shape[0], states.shape[0], pp,
+                                                  priority.shape[0], nv.current_stream()))
+
+    def sample_indices(self, u: torch.Tensor) -> torch.Tensor:
+        leaf = torch.empty(u.numel(), dtype=torch.int64, device=self.device)
+        nv.check(self.lib.r2d2_replay_sample(self._h, nv.dptr(u), u.numel(), nv.dptr(leaf, torch.int64), None, None,
+                                             None, None, None, nv.current_stream()))
+        return leaf
+
+    def sample_into(self, eng: LearnerEngine, generator: torch.Generator | None = None, u: torch.Tensor | None = None):
+        """Draw eng.cfg.batch starts and gather the time-major batch straight into the engine's buffers."""
+        if u is None:
+            eng.uniforms.copy_(torch.rand(eng.cfg.batch, device=self.device, generator=generator))
+        else:
+            eng.uniforms.copy_(u)
+        nv.check(self.lib.r2d2_replay_sample(self._h, nv.dptr(eng.uniforms), eng.cfg.batch,
+                                             nv.dptr(eng.leaf_idx, torch.int64), nv.dptr(eng.obs), nv.dptr(eng.act),
+                                             nv.dptr(eng.rew), nv.dptr(eng.term), nv.dptr(eng.states),
+                                             nv.current_stream()))
+
+    def update_priorities(self, leaf_idx: torch.Tensor, prio: torch.Tensor):
+        nv.check(self.lib.r2d2_replay_update_priorities(self._h, nv.dptr(leaf_idx, torch.int64), nv.dptr(prio),
+                                                        leaf_idx.numel(), nv.current_stream()))
+
+    def stats(self) -> dict:
+        st = nv.ReplayStats()
+        nv.check(self.lib.r2d2_replay_stats(self._h, byref(st), nv.current_stream()))
+        return {k: getattr(st, k) for k, _ in nv.ReplayStats._fields_}
+
+    def decode(self, leaf_idx):
+        leaf = np.ascontiguousarray(np.asarray(leaf_idx.cpu() if isinstance(leaf_idx, torch.Tensor) else leaf_idx),
+                                    dtype=np.int64)
+        ep = np.empty_like(leaf)
+        sq = np.empty_like(leaf)
+        nv.check(self.lib.r2d2_replay_decode(self._h, leaf.ctypes.data_as(c_void_p), leaf.size,
+                                             ep.ctypes.data_as(c_void_p), sq.ctypes.data_as(c_void_p)))
+        return ep, sq
+
+    def tree_level(self, level: int) -> torch.Tensor:
+        p, n = c_void_p(), c_longlong()
+        nv.check(self.lib.r2d2_replay_tree_level(self._h, level, byref(p), byref(n)))
+        return nv.view_f32(p.value, (n.value,), self.device)
