@@ -150,8 +150,9 @@ def test_net_forward_backward(nv, O, A, H, B, T, repeat, critic, first_row):
     assert rel_l2(out.cpu().numpy(), out_ref) < TOL
     grads = torch.zeros(npar, device="cuda")
     d_act = torch.zeros((T, B, A), device="cuda") if critic else None
+    d_out_dev = dev(d_out_rows)
     nv.check(lib.r2d2_lstm_net_backward(nv.byref(shape), nv.dptr(dparams), nv.dptr(dobs),
-                                        nv.dptr(dact) if critic else None, nv.dptr(dev(d_out_rows)), T, B, repeat,
+                                        nv.dptr(dact) if critic else None, nv.dptr(d_out_dev), T, B, repeat,
                                         first_row, nv.dptr(grads), nv.dptr(d_act), nv.dptr(ws), nv.current_stream()))
     torch.cuda.synchronize()
     g = grads.cpu().numpy()
@@ -196,7 +197,8 @@ def test_td_priority(nv, L, B, A, Bn, n):
                                                             n_step=n, gamma=0.997)
     o = {k: torch.zeros(s, device="cuda") for k, s in (("y", (L, B, A)), ("dq", (L, B, A)), ("td", (L, B)),
                                                         ("p", (B,)), ("loss", (1,)))}
-    nv.check(nv.lib().r2d2_td_priority(nv.dptr(dev(q)), nv.dptr(dev(qn)), nv.dptr(dev(rew)), nv.dptr(dev(term)), L, B,
+    dq_, dqn_, drew_, dterm_ = dev(q), dev(qn), dev(rew), dev(term)   # keep alive across the async launch
+    nv.check(nv.lib().r2d2_td_priority(nv.dptr(dq_), nv.dptr(dqn_), nv.dptr(drew_), nv.dptr(dterm_), L, B,
                                        A, Bn, n, 0.997, 0.9, nv.dptr(o["y"]), nv.dptr(o["dq"]), nv.dptr(o["td"]),
                                        nv.dptr(o["p"]), nv.dptr(o["loss"]), nv.current_stream()))
     torch.cuda.synchronize()
@@ -218,7 +220,8 @@ def test_adam_matches_torch(nv):
         grad = torch.randn(n, generator=g) * (0.1 ** step)
         ref_p.grad = grad.clone()
         opt.step()
-        nv.check(nv.lib().r2d2_adam_step(nv.dptr(p), nv.dptr((2 * grad).cuda()), nv.dptr(m), nv.dptr(v), n, step, 1e-3,
+        g2 = (2 * grad).cuda()
+        nv.check(nv.lib().r2d2_adam_step(nv.dptr(p), nv.dptr(g2), nv.dptr(m), nv.dptr(v), n, step, 1e-3,
                                          0.9, 0.999, 1e-8, 0.5, nv.current_stream()))
     torch.cuda.synchronize()
     assert rel_l2(p.cpu().numpy() - p0.numpy(), ref_p.detach().numpy() - p0.numpy()) < 1e-5
