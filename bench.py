@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py - learner sequence-steps/sec (batch x seq_len per learner iteration) of the B200-native
+learner hot path, BASELINE.json configs[1]: synthetic obs=17 act=6 hidden=256 seq_len=80 burn_in=40
+batch=256 per GPU (weak scaling: every rank owns a replay shard and a batch of 256; gradients are
+all-reduced over NCCL at the two optimiser steps).
+
+  python bench.py --gpus N --steps K --warmup W          # torchrun launches one process per GPU for N > 1
+  python bench.py --impl reference ...                   # the reference's CPU implementation (oracle port)
+
+A step = one pass of learner.py:84-139: prioritized sample from the HBM replay shard -> gather ->
+target/online chains -> TD/priority kernel -> critic BPTT + Adam -> actor chain -> DPG backward + Adam
+-> priority write-back into the sum tree.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pytorch-r2d2-dpg_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CONFIGS = {
+    # BASELINE.json configs[0] shapes (reference as-is, walker sizes) / configs[1] (headline) / configs[2]
+    "cfg1": dict(obs=24, act=6, hidden=128, batch=32, burn_in=20, learning=40, n_step=5),
+    "cfg2": dict(obs=17, act=6, hidden=256, batch=256, burn_in=40, learning=80, n_step=5),
+    "cfg3": dict(obs=376, act=17, hidden=512, batch=512, burn_in=40, learning=80, n_step=5),
+}
+METRIC = "learner sequence-steps/sec (batch x seq_len)"
+
+
+def lstm_flops_per_iteration(c):
+    """FLOP_lstm = 16*B*H^2*(5*Bn + 13*L + 2*n) (necessary cell-steps, fwd + bwd)."""
+    return 16.0 * c["batch"] * c["hidden"] ** 2 * (5 * c["burn_in"] + 13 * c["learning"] + 2 * c["n_step"])
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"],
+                "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_replay(engine, cfg, n_episodes, episode_len, seed, device):
+    rng = np.random.default_rng(seed)
+    n_rows = episode_len + cfg.n_step
+    rp = engine.DeviceReplay(cfg, capacity_rows=n_episodes * n_rows, device=device)
+    for _ in range(n_episodes):
+        term = np.zeros(n_rows, np.float32)
+        term[episode_len:] = 1
+        obs = rng.standard_normal((n_rows, cfg.obs), dtype=np.float32)
+        act = rng.uniform(-1, 1, (n_rows, cfg.act)).astype(np.float32)
+        rew = rng.standard_normal(n_rows, dtype=np.float32)
+        obs[episode_len:] = 0
+        act[episode_len:] = 0
+        rew[episode_len:] = 0
+        states = 0.1 * rng.standard_normal((episode_len, 4, 2, cfg.hidden), dtype=np.float32)
+        prio = rng.uniform(0.01, 1.0, episode_len - (cfg.burn_in + cfg.learning)).astype(np.float32)
+        rp.add_episode(obs, act, rew, term, states, prio)
+    return rp
+
+
+def time_cpu_port(c, steps, warmup, threads):
+    """The reference's CPU implementation of the path (oracle/ref_port.py: same torch CPU operators,
+    python loops, autograd, Adam, two-level WeightedRandomSampler draw) on this box's host cores."""
+    from oracle import ref_port
+    torch.set_num_threads(threads)
+    pc = ref_port.PathConfig(**c)
+    lr = ref_port.PortLearner(pc, seed=1)
+    rp = ref_port.synthetic_replay(pc, n_episodes=max(8, (2 * c["batch"]) // 100 + 8), episode_len=250, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ep, sq, batch = rp.sample()
+        out = lr.iteration(batch, keep_tensors=False)
+        rp.write_back(ep, sq, out["priority"])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return c["batch"] * c["learning"] / sec, sec
+
+
+def run_reference(args, c):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    value, sec = time_cpu_port(c, args.steps, args.warmup, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "seq-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: " + " ".join(f"{k}={v}" for k, v in c.items()),
+                       "note": "reference CPU learner (oracle/ref_port.py port; /root/reference is python and not "
+                               "present on this box), full batch per step"},
+            "cpu_baseline": {"value": value, "unit": "seq-steps/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} full learner iterations at batch {c['batch']} after {args.warmup} warm-up"},
+            "e2e": {"value": value, "unit": "seq-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--episodes", type=int, default=384, help="episodes in the per-GPU replay shard")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    args = ap.parse_args()
+    c = CONFIGS[args.config]
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args, c)
+
+    from r2d2_b200 import engine, native as nv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = engine.PathConfig(**c)
+    eng = engine.LearnerEngine(cfg, device=dev, seed=1)
+    eng.enable_data_parallel()
+    ep_len = 250
+    rp = build_replay(engine, cfg, args.episodes, ep_len, seed=100 + rank, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    B, L, T, O, A, H = cfg.batch, cfg.learning, cfg.rows, cfg.obs, cfg.act, cfg.hidden
+
+    def step_resident():
+        rp.sample_into(eng, generator=gen)
+        eng.step()
+        rp.update_priorities(eng.leaf_idx, eng.priority)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * B * L / (ms * 1e-3)
+    launches_per_step = eng.launches_per_iteration + 6 + 1   # + sample/gather kernels + tree update
+
+    # ---- e2e: the same iteration fed from HOST buffers (the reference's boundary: replay_memory.py:123-133
+    # copies the sampled batch to the device each iteration, learner.py:135 reads the TD result back)
+    n_pool = 4
+    pool = []
+    for i in range(n_pool):
+        rp.sample_into(eng, generator=gen)
+        torch.cuda.synchronize()
+        pool.append({k: getattr(eng, k).cpu().pin_memory() for k in ("obs", "act", "rew", "term", "states")})
+    host_prio = torch.empty(B, dtype=torch.float32).pin_memory()
+    host_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * 4 for v in pool[0].values())
+    d2h = (B + 2) * 4
+
+    def step_host(i):
+        hb = pool[i % n_pool]
+        for k, v in hb.items():
+            getattr(eng, k).copy_(v, non_blocking=True)
+        eng.step()
+        host_prio.copy_(eng.priority, non_blocking=True)
+        host_loss.copy_(eng.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the host consumes the priorities every iteration
+
+    for i in range(args.warmup):
+        step_host(i)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step_host(i)
+    ev1.record()
+    barrier()
+    ms_e2e = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * L / (float(ms_e2e.item()) * 1e-3)
+
+    # ---- roofline of the dominant kernel: the persistent LSTM scan (serial half of every cell step).
+    # algorithmic FLOPs per launch = 2 * B * H * 4H per cell step x S steps (F_cell = 16 B H^2 covers
+    # both halves; the hoisted x*W_ih half runs in gemm_f32).  Timed alone with CUDA events on the launch stream.
+    peaks = measured_peaks()
+    S = cfg.burn_in + cfg.n_step + cfg.learning
+    gin = torch.randn(S, B, 4 * H, device=dev) * 0.5
+    whh = (torch.rand(4 * H, H, device=dev) * 2 - 1) / np.sqrt(4 * H)
+    gates = torch.empty_like(gin)
+    hs = torch.empty(S + 1, B, H, device=dev)
+    cs = torch.empty(S + 1, B, H, device=dev)
+    lib, st = nv.lib(), nv.current_stream()
+    scratch = torch.empty(B * 4 * H, device=dev)
+
+    def scan():
+        nv.check(lib.r2d2_lstm_scan_forward(nv.dptr(gin), nv.dptr(whh), None, None, nv.dptr(gates), nv.dptr(hs),
+                                            nv.dptr(cs), None, S, B, H, 1, nv.dptr(scratch), st))
+    for _ in range(3):
+        scan()
+    torch.cuda.synchronize()
+    reps = 10
+    ev0.record()
+    for _ in range(reps):
+        scan()
+    ev1.record()
+    torch.cuda.synchronize()
+    scan_ms = ev0.elapsed_time(ev1) / reps
+    scan_flops = 2.0 * B * H * 4 * H * S
+    achieved = scan_flops / (scan_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "scan_fwd_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "lstm_scan_fwd_kernel (persistent cluster LSTM scan, %d steps)" % S, "bound": "tensor",
+                "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
+                "traffic": traffic, "peak_source": peaks["source"] + " bf16 dense burst (kernel timed alone)",
+                "us_per_step": scan_ms * 1e3 / S,
+                "whole_iteration": {"lstm_flops": lstm_flops_per_iteration(c),
+                                    "achieved_tflops": lstm_flops_per_iteration(c) / (ms * 1e-3) / 1e12,
+                                    "frac_of_sustained_peak": lstm_flops_per_iteration(c) / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"]}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sec = time_cpu_port(c, args.cpu_steps, 1, threads)
+        cpu_baseline = {"value": v, "unit": "seq-steps/s", "cores": threads, "kind": "port",
+                        "sample": f"{args.cpu_steps} full learner iterations at batch {B} after 1 warm-up ({sec:.2f} s each)"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "seq-steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 (bf16x3 split tensor-core MMAs, fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": f"{args.config}: " + " ".join(f"{k}={v}" for k, v in c.items()) + " per GPU",
+                           "parallelism": f"dp{world}", "global_batch": world * B,
+                           "replay_shard": f"{args.episodes} episodes x {ep_len + cfg.n_step} rows per GPU in HBM",
+                           "l2": "inputs larger than L2: every step streams >1 GB of activations and gathers its batch "
+                                 "from a multi-GB replay shard"},
+                "e2e": {"value": e2e_value, "unit": "seq-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,19 @@ int r2d2_lstm_net_backward(const r2d2_net_shape* shape, const float* params, con
                            const float* d_out, int T, int B, int repeat, int head_first_row, float* grads,
                            float* d_act, float* workspace, r2d2_stream_t stream);
 
+/* The serial scan alone (the persistent-RNN kernel; bench.py times it for the roofline line):
+ * gin [T,B,4H] pre-activation input projection, whh [4H,H], h0/c0 [B,H] or NULL; outputs gates [T*repeat,B,4H]
+ * (may alias gin when repeat == 1), hs/cs [T*repeat+1,B,H], head_in [T,B,H] or NULL.  scratch: NULL for
+ * H in {32,64,128,256}, else [B,4H] floats. */
+int r2d2_lstm_scan_forward(const float* gin, const float* whh, const float* h0, const float* c0, float* gates,
+                           float* hs, float* cs, float* head_in, int T, int B, int H, int repeat, float* scratch,
+                           r2d2_stream_t stream);
+/* BPTT twin: dgates [S,B,4H] (may alias gates), dgin [T,B,4H] (only when repeat > 1), dh_head [*,B,H] or NULL
+ * consumed from step head_first_step on.  scratch: NULL for the cluster sizes, else [2,B,H]. */
+int r2d2_lstm_scan_backward(const float* gates, const float* hs, const float* cs, const float* whh,
+                            const float* dh_head, int head_first_step, float* dgates, float* dgin, int T, int B,
+                            int H, int repeat, float* scratch, r2d2_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused n-step target + value rescaling + TD loss gradient + sequence priority
  * (learner.py:107-111,135-138; utils.py:17-21).  q, q_next [L,B,A]; rew, term [T',B].

@@ -94,6 +94,24 @@ int r2d2_lstm_net_backward(const r2d2_net_shape* shape, const float* params, con
                       S(stream));
 }
 
+int r2d2_lstm_scan_forward(const float* gin, const float* whh, const float* h0, const float* c0, float* gates,
+                           float* hs, float* cs, float* head_in, int T, int B, int H, int repeat, float* scratch,
+                           r2d2_stream_t stream) {
+  ScanFwdParams p;
+  p.gin = gin; p.whh = whh; p.h0 = h0; p.c0 = c0; p.gates = gates; p.hs = hs; p.cs = cs; p.head_in = head_in;
+  p.T = T; p.B = B; p.H = H; p.repeat = repeat; p.scratch = scratch;
+  return lstm_scan_forward(p, S(stream));
+}
+
+int r2d2_lstm_scan_backward(const float* gates, const float* hs, const float* cs, const float* whh,
+                            const float* dh_head, int head_first_step, float* dgates, float* dgin, int T, int B,
+                            int H, int repeat, float* scratch, r2d2_stream_t stream) {
+  ScanBwdParams p;
+  p.gates = gates; p.hs = hs; p.cs = cs; p.whh = whh; p.dh_head = dh_head; p.head_first_step = head_first_step;
+  p.dgates = dgates; p.dgin = dgin; p.T = T; p.B = B; p.H = H; p.repeat = repeat; p.scratch = scratch;
+  return lstm_scan_backward(p, S(stream));
+}
+
 int r2d2_td_priority(const float* q, const float* q_next, const float* rew, const float* term, int L, int B,
                      int A, int burn_in, int n_step, float gamma, float eta, float* target, float* dq,
                      float* td_sq, float* priority, float* critic_loss, r2d2_stream_t stream) {

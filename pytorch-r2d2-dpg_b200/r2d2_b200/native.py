@@ -71,6 +71,10 @@ SIGNATURES = {
                                       c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "r2d2_lstm_net_backward": (c_int, [POINTER(NetShape), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r2d2_lstm_scan_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "r2d2_lstm_scan_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                        c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "r2d2_td_priority": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                  c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r2d2_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_float, c_float,
