@@ -104,15 +104,45 @@ def build_replay(engine, cfg, n_episodes, episode_len, seed, device):
     return rp
 
 
-def time_cpu_port(c, steps, warmup, threads):
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def pick_cpu_threads(c):
+    """torch CPU ops of this size (batch x hidden LSTMCell steps) stop scaling - and can collapse - long
+    before a 100+ core box is full, so probe a few thread counts on a short LSTMCell fwd+bwd loop and keep
+    the fastest: the baseline gets the best setting this host offers, and `cores` reports it."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({t for t in (4, 8, 16, 32, 64, ncpu) if t <= ncpu})
+    cell = torch.nn.LSTMCell(c["hidden"], c["hidden"])
+    x = torch.randn(c["batch"], c["hidden"])
+    best, best_t = cands[0], float("inf")
+    for t in cands:
+        torch.set_num_threads(t)
+        for rep in range(2):
+            t0 = time.perf_counter()
+            h = cx = torch.zeros(c["batch"], c["hidden"])
+            for _ in range(12):
+                h, cx = cell(x, (h, cx))
+            h.sum().backward()
+            dt = time.perf_counter() - t0
+        log(f"cpu thread probe: {t} threads -> {dt * 1e3:.1f} ms")
+        if dt < best_t:
+            best, best_t = t, dt
+    return best
+
+
+def time_cpu_port(c, steps, warmup, threads=None, budget_s=150.0):
     """The reference's CPU implementation of the path (oracle/ref_port.py: same torch CPU operators,
-    python loops, autograd, Adam, two-level WeightedRandomSampler draw) on this box's host cores."""
+    python loops, autograd, Adam, two-level WeightedRandomSampler draw) on this box's host cores.
+    Stops early (after >= 1 timed iteration) when `budget_s` of wall clock is spent."""
     from oracle import ref_port
+    threads = threads or pick_cpu_threads(c)
     torch.set_num_threads(threads)
     pc = ref_port.PathConfig(**c)
     lr = ref_port.PortLearner(pc, seed=1)
     rp = ref_port.synthetic_replay(pc, n_episodes=max(8, (2 * c["batch"]) // 100 + 8), episode_len=250, seed=0)
-    times = []
+    times, t_start = [], time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         ep, sq, batch = rp.sample()
@@ -120,16 +150,18 @@ def time_cpu_port(c, steps, warmup, threads):
         rp.write_back(ep, sq, out["priority"])
         if i >= warmup:
             times.append(time.perf_counter() - t0)
+        log(f"cpu port iteration {i}: {time.perf_counter() - t0:.2f} s")
+        if times and time.perf_counter() - t_start > budget_s:
+            break
     sec = float(np.mean(times))
-    return c["batch"] * c["learning"] / sec, sec
+    return c["batch"] * c["learning"] / sec, sec, threads, len(times)
 
 
 def run_reference(args, c):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    value, sec = time_cpu_port(c, args.steps, args.warmup, threads)
+    value, sec, threads, done = time_cpu_port(c, args.steps, args.warmup, budget_s=240.0)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "seq-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -137,7 +169,8 @@ def run_reference(args, c):
                        "note": "reference CPU learner (oracle/ref_port.py port; /root/reference is python and not "
                                "present on this box), full batch per step"},
             "cpu_baseline": {"value": value, "unit": "seq-steps/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} full learner iterations at batch {c['batch']} after {args.warmup} warm-up"},
+                             "sample": f"{done} full learner iterations at batch {c['batch']} after {args.warmup} warm-up, "
+                                       f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)"},
             "e2e": {"value": value, "unit": "seq-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -174,6 +207,7 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    log(f"world={world} rank={rank}: building engine + replay shard")
     cfg = engine.PathConfig(**c)
     eng = engine.LearnerEngine(cfg, device=dev, seed=1)
     eng.enable_data_parallel()
@@ -192,6 +226,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log("warm-up (HBM-resident arm)")
     for _ in range(args.warmup):
         step_resident()
     barrier()
@@ -214,6 +249,7 @@ def main():
     value = world * B * L / (ms * 1e-3)
     launches_per_step = eng.launches_per_iteration + 6 + 1   # + sample/gather kernels + tree update
 
+    log(f"resident arm: {ms:.3f} ms/step; e2e arm")
     # ---- e2e: the same iteration fed from HOST buffers (the reference's boundary: replay_memory.py:123-133
     # copies the sampled batch to the device each iteration, learner.py:135 reads the TD result back)
     n_pool = 4
@@ -249,6 +285,7 @@ def main():
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * B * L / (float(ms_e2e.item()) * 1e-3)
 
+    log("roofline: timing the scan kernel alone")
     # ---- roofline of the dominant kernel: the persistent LSTM scan (serial half of every cell step).
     # algorithmic FLOPs per launch = 2 * B * H * 4H per cell step x S steps (F_cell = 16 B H^2 covers
     # both halves; the hoisted x*W_ih half runs in gemm_f32).  Timed alone with CUDA events on the launch stream.
@@ -294,10 +331,11 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, sec = time_cpu_port(c, args.cpu_steps, 1, threads)
+        log("cpu_baseline leg (oracle port on host cores)")
+        v, sec, threads, done = time_cpu_port(c, args.cpu_steps, 1, budget_s=60.0)
         cpu_baseline = {"value": v, "unit": "seq-steps/s", "cores": threads, "kind": "port",
-                        "sample": f"{args.cpu_steps} full learner iterations at batch {B} after 1 warm-up ({sec:.2f} s each)"}
+                        "sample": f"{done} full learner iterations at batch {B} after 1 warm-up ({sec:.2f} s each), "
+                                  f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)"}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "seq-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
