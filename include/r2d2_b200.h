@@ -92,6 +92,12 @@ int r2d2_lstm_scan_backward(const float* gates, const float* hs, const float* cs
                             const float* dh_head, int head_first_step, float* dgates, float* dgin, int T, int B,
                             int H, int repeat, float* scratch, r2d2_stream_t stream);
 
+/* scan implementation switch for A/B checks: 1 = tcgen05/TMEM (default), 0 = mma.sync v1 kernels */
+int r2d2_set_scan_impl(int impl);
+int r2d2_get_scan_impl(void);
+/* *status != 0 if a bounded mbarrier wait inside a tcgen05 scan kernel ever timed out; synchronises the stream */
+int r2d2_scan_status(int* status, r2d2_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused n-step target + value rescaling + TD loss gradient + sequence priority
  * (learner.py:107-111,135-138; utils.py:17-21).  q, q_next [L,B,A]; rew, term [T',B].
@@ -144,6 +150,7 @@ int r2d2_replay_update_priorities(r2d2_replay_t* r, const long long* leaf_idx, c
 
 typedef struct {
   long long n_episodes, n_rows_used, sequence_counter, capacity_rows, tree_levels, tree_nodes;
+  long long last_row_start;        /* first row of the most recently added episode */
   double total_priority;
 } r2d2_replay_stats_t;
 int r2d2_replay_stats(r2d2_replay_t* r, r2d2_replay_stats_t* out, r2d2_stream_t stream); /* synchronises */

@@ -112,6 +112,10 @@ int r2d2_lstm_scan_backward(const float* gates, const float* hs, const float* cs
   return lstm_scan_backward(p, S(stream));
 }
 
+int r2d2_set_scan_impl(int impl) { lstm_scan_set_impl(impl); return R2D2_OK; }
+int r2d2_get_scan_impl(void) { return lstm_scan_get_impl(); }
+int r2d2_scan_status(int* status, r2d2_stream_t stream) { return lstm_scan_error_status(status, S(stream)); }
+
 int r2d2_td_priority(const float* q, const float* q_next, const float* rew, const float* term, int L, int B,
                      int A, int burn_in, int n_step, float gamma, float eta, float* target, float* dq,
                      float* td_sq, float* priority, float* critic_loss, r2d2_stream_t stream) {

@@ -9,6 +9,7 @@
 //   backward: P[H x NB] = W_slice^T[H x 128] * dG_s^T  -> reduce-scatter of fp32 partials via DSMEM
 // Tensor cores: mma.sync bf16, 3 passes (hi*hi, lo*hi, hi*lo), fp32 accumulate.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "gemm.cuh"
 #include "lstm_scan.cuh"
@@ -527,6 +528,16 @@ int bwd_dispatch(const ScanBwdParams& p, cudaStream_t stream) {
 
 bool lstm_scan_cluster_supported(int H) { return H == 32 || H == 64 || H == 128 || H == 256; }
 
+static int g_scan_impl = -1;
+void lstm_scan_set_impl(int impl) { g_scan_impl = impl ? 1 : 0; }
+int lstm_scan_get_impl() {
+  if (g_scan_impl < 0) {
+    const char* e = getenv("R2D2_SCAN_IMPL");
+    g_scan_impl = (e && (e[0] == 'm' || e[0] == '0')) ? 0 : 1;
+  }
+  return g_scan_impl;
+}
+
 size_t lstm_scan_fwd_scratch_floats(int B, int H) {
   return lstm_scan_cluster_supported(H) ? 0 : (size_t)B * 4 * H;
 }
@@ -538,6 +549,7 @@ int lstm_scan_forward(const ScanFwdParams& p, cudaStream_t stream) {
   R2D2_REQUIRE(p.gin && p.whh && p.gates && p.hs && p.cs, "null pointer");
   R2D2_REQUIRE(p.T > 0 && p.B > 0 && p.H > 0 && p.repeat >= 1, "shape");
   R2D2_REQUIRE(p.repeat == 1 || p.gates != p.gin, "gates must not alias gin when repeat > 1");
+  if (lstm_scan_cluster_supported(p.H) && lstm_scan_get_impl() == 1) return lstm_scan_forward_tc(p, stream);
   switch (p.H) {
     case 32: return fwd_dispatch<32>(p, stream);
     case 64: return fwd_dispatch<64>(p, stream);
@@ -552,6 +564,7 @@ int lstm_scan_backward(const ScanBwdParams& p, cudaStream_t stream) {
   R2D2_REQUIRE(p.gates && p.hs && p.cs && p.whh && p.dgates, "null pointer");
   R2D2_REQUIRE(p.T > 0 && p.B > 0 && p.H > 0 && p.repeat >= 1, "shape");
   R2D2_REQUIRE(p.repeat == 1 || (p.dgin && p.dgin != p.dgates), "dgin buffer required when repeat > 1");
+  if (lstm_scan_cluster_supported(p.H) && lstm_scan_get_impl() == 1) return lstm_scan_backward_tc(p, stream);
   switch (p.H) {
     case 32: return bwd_dispatch<32>(p, stream);
     case 64: return bwd_dispatch<64>(p, stream);

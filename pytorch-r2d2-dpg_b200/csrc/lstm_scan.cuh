@@ -42,4 +42,13 @@ int lstm_scan_backward(const ScanBwdParams& p, cudaStream_t stream);
 size_t lstm_scan_fwd_scratch_floats(int B, int H);
 size_t lstm_scan_bwd_scratch_floats(int B, int H);
 
+// implementation of the cluster kernels: 1 = tcgen05/TMEM (default), 0 = mma.sync (v1, kept for A/B checks).
+// Initialised from the environment variable R2D2_SCAN_IMPL ("tc" | "mma") on first use.
+void lstm_scan_set_impl(int impl);
+int lstm_scan_get_impl();
+int lstm_scan_forward_tc(const ScanFwdParams& p, cudaStream_t stream);
+int lstm_scan_backward_tc(const ScanBwdParams& p, cudaStream_t stream);
+// nonzero if a bounded mbarrier wait of a tcgen05 scan kernel ever timed out (protocol bug); synchronises the stream
+int lstm_scan_error_status(int* out, cudaStream_t stream);
+
 }  // namespace r2d2

@@ -1,0 +1,528 @@
+// tcgen05 / TMEM version of the persistent cluster LSTM scan (forward + BPTT) for sm_100a.
+//
+// Same decomposition as the mma.sync kernels in lstm_scan.cu (cluster of C = H/32 CTAs per NB batch rows,
+// CTA `rank` owns hidden units [32 rank, 32 rank + 32) = 128 gate rows of W_hh), but
+//   * the W_hh slice lives in SHARED memory as bf16 hi/lo planes in the UMMA K-major core-matrix layout and
+//     is read directly by the 5th-gen tensor cores: per cell step one elected thread issues
+//     (H/16) x 3 tcgen05.mma (M=128 gate rows, N=NB batch columns, K=16; passes lo*hi, hi*lo, hi*hi) that
+//     accumulate in TMEM; tcgen05.commit -> mbarrier tells the epilogue warps;
+//   * the epilogue reads the accumulator with tcgen05.ld (lane = gate row), finishes the LSTM cell in
+//     registers and stages h_t (bf16 hi/lo, already in the operand layout of the next step);
+//   * the h_t all-gather inside the cluster is 2*C bulk shared->remote-shared copies
+//     (cp.async.bulk.shared::cluster) that complete transaction bytes on the DESTINATION's mbarrier: no
+//     cluster-wide barrier and no memory fence on the global stores of gates / h / c on the serial chain
+//     (the v1 kernel spent 24% of its samples in the barrier's release fence, profiles/r01_*).
+// Backward: P[H x NB] = W_slice^T [H x 128] * dG^T via tcgen05, fp32 partial sums reduce-scattered with bulk copies.
+#include <cooperative_groups.h>
+
+#include "lstm_scan.cuh"
+#include "tc05.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace r2d2 {
+
+int* scan_error_flag();  // device int, 0 = ok (defined below)
+
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int GT_LD = 128 + 4;
+
+__device__ __forceinline__ float accurate_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void split8_store(const float4 v0, const float4 v1, unsigned char* hi_dst, unsigned char* lo_dst) {
+  uint4 h, l;
+  split_pack2(v0.x, v0.y, h.x, l.x);
+  split_pack2(v0.z, v0.w, h.y, l.y);
+  split_pack2(v1.x, v1.y, h.z, l.z);
+  split_pack2(v1.z, v1.w, h.w, l.w);
+  *reinterpret_cast<uint4*>(hi_dst) = h;
+  *reinterpret_cast<uint4*>(lo_dst) = l;
+}
+
+template <int H, int NB>
+struct TcFwdSmem {
+  static constexpr int C = H / 32, KC = H / 8;
+  static constexpr int A_PLANE = KC * 128 * 16;   // bytes: [k-chunk][row 0..127][8 bf16]
+  static constexpr int HB_PLANE = KC * NB * 16;   // bytes: [k-chunk][n][8 bf16]
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_HB = 2 * A_PLANE;                     // [buf][plane]
+  static constexpr int OFF_GT = OFF_HB + 4 * HB_PLANE;           // fp32 [NB][GT_LD]
+  static constexpr int OFF_HSTAGE = OFF_GT + NB * GT_LD * 4;     // [dbuf][plane][4 chunks][NB][8] bf16
+  static constexpr int HSTAGE_PLANE = 4 * NB * 16;               // bytes of one CTA's slice of one plane
+  static constexpr int OFF_BAR = OFF_HSTAGE + 4 * HSTAGE_PLANE;  // 3 mbarriers + tmem slot + dead flag
+  static constexpr int BYTES = OFF_BAR + 64;
+  static_assert(BYTES <= 232448, "forward scan tile does not fit in 227 KB of shared memory");
+};
+
+template <int H, int NB>
+__global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwdParams p, int* err) {
+  using SM = TcFwdSmem<H, NB>;
+  constexpr int C = SM::C, KC = SM::KC, KS = H / 16, NT = NB / 8;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / C) * NB;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int B = p.B, S = p.T * p.repeat;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* a_hi = smem + SM::OFF_A;
+  unsigned char* a_lo = a_hi + SM::A_PLANE;
+  unsigned char* hb = smem + SM::OFF_HB;
+  float* gt = reinterpret_cast<float*>(smem + SM::OFF_GT);
+  unsigned char* hstage = smem + SM::OFF_HSTAGE;
+  uint64_t* h_full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);  // [2]
+  uint64_t* mma_done = h_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  if (tid == 0) {
+    tc::mbar_init(&h_full[0], 1);
+    tc::mbar_init(&h_full[1], 1);
+    tc::mbar_init(mma_done, 1);
+    tc::fence_mbar_init_cluster();
+    *dead = 0;
+  }
+  if (w == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, 32 > NB ? 32 : NB); }
+
+  // ---- W_hh slice -> shared (bf16 hi/lo, UMMA K-major core matrices): row r = gate*32 + unit
+  for (int idx = tid; idx < 128 * KC; idx += TC_THREADS) {
+    const int r = idx & 127, kc = idx >> 7;
+    const float* src = p.whh + (size_t)((r >> 5) * H + rank * 32 + (r & 31)) * H + kc * 8;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+    split8_store(v0, v1, a_hi + kc * 2048 + r * 16, a_lo + kc * 2048 + r * 16);
+  }
+  // ---- initial h tile (all H units of my NB rows) -> operand buffer 0
+  for (int idx = tid; idx < NB * KC; idx += TC_THREADS) {
+    const int n = idx % NB, kc = idx / NB, b = b0 + n;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (b < B && p.h0) {
+      const float* src = p.h0 + (size_t)b * H + kc * 8;
+      v0 = __ldg(reinterpret_cast<const float4*>(src));
+      v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+    }
+    split8_store(v0, v1, hb + 0 * SM::HB_PLANE + kc * NB * 16 + n * 16, hb + 1 * SM::HB_PLANE + kc * NB * 16 + n * 16);
+  }
+  const int ug = rank * 32 + lane;
+  float cst[NT];
+#pragma unroll
+  for (int e = 0; e < NT; ++e) {
+    const int b = b0 + w + 8 * e;
+    cst[e] = 0.f;
+    if (b < B) {
+      const float hv = p.h0 ? __ldg(p.h0 + (size_t)b * H + ug) : 0.f;
+      const float cv = p.c0 ? __ldg(p.c0 + (size_t)b * H + ug) : 0.f;
+      p.hs[(size_t)b * H + ug] = hv;
+      p.cs[(size_t)b * H + ug] = cv;
+      cst[e] = cv;
+    }
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster.sync();  // every CTA's barriers are initialised before any remote copy can target them
+
+  const uint32_t idesc = tc::make_idesc_bf16_f32(128, NB);
+  const uint32_t a_hi_addr = tc::smem_u32(a_hi), a_lo_addr = tc::smem_u32(a_lo), hb_addr = tc::smem_u32(hb);
+  const size_t gstride = (size_t)4 * H;
+  constexpr uint32_t STEP_TX = (uint32_t)C * 2u * (uint32_t)SM::HSTAGE_PLANE;
+
+  for (int s = 0; s < S; ++s) {
+    const int cur = s & 1, nxt = cur ^ 1;
+    const int t = s / p.repeat;
+
+    float gpre[NT][4];
+#pragma unroll
+    for (int e = 0; e < NT; ++e) {
+      const int b = b0 + w + 8 * e;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        gpre[e][q] = (b < B) ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;  // plain load: gates may alias gin
+    }
+
+    if (tid == 0) {
+      if (s + 1 < S) tc::mbar_arrive_expect_tx(&h_full[nxt], STEP_TX);  // h_s from all C CTAs lands in buffer nxt
+      if (s > 0 && !*dead) {
+        if (!tc::mbar_wait(&h_full[cur], ((s - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 1); }
+      }
+      tc::fence_after_thread_sync();
+      const uint32_t hb_hi = hb_addr + (cur * 2 + 0) * SM::HB_PLANE, hb_lo = hb_addr + (cur * 2 + 1) * SM::HB_PLANE;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint64_t da_hi = tc::make_smem_desc(a_hi_addr + ks * 4096, 2048, 128);
+        const uint64_t da_lo = tc::make_smem_desc(a_lo_addr + ks * 4096, 2048, 128);
+        const uint64_t db_hi = tc::make_smem_desc(hb_hi + ks * 2 * NB * 16, NB * 16, 128);
+        const uint64_t db_lo = tc::make_smem_desc(hb_lo + ks * 2 * NB * 16, NB * 16, 128);
+        tc::mma_bf16_ss(tmem_base, da_lo, db_hi, idesc, ks > 0);
+        tc::mma_bf16_ss(tmem_base, da_hi, db_lo, idesc, true);
+        tc::mma_bf16_ss(tmem_base, da_hi, db_hi, idesc, true);
+      }
+      tc::mma_commit(mma_done);
+    }
+    if (!*dead) {
+      if (!tc::mbar_wait(mma_done, s & 1)) { *dead = 1; atomicExch(err, 2); }
+    }
+    tc::fence_after_thread_sync();
+    __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the spin wait
+
+    // ---- accumulator -> gate tile: warp w reads TMEM lanes 32*(w&3).. (gate w&3, unit = lane), column half w>>2
+    {
+      const int q = w & 3, ch = w >> 2;
+#pragma unroll
+      for (int part = 0; part < NB / 16; ++part) {
+        const int c0 = ch * (NB / 2) + part * 8;
+        float v[8];
+        tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gt[(c0 + j) * GT_LD + q * 32 + lane] = v[j];
+      }
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+
+    // ---- pointwise LSTM cell: thread = (unit = lane, batch column n = w + 8e); coalesced along units
+    unsigned char* hs_buf = hstage + (s & 1) * 2 * SM::HSTAGE_PLANE;
+#pragma unroll
+    for (int e = 0; e < NT; ++e) {
+      const int n = w + 8 * e, b = b0 + n;
+      __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+      if (b < B) {
+        const float* gr = gt + n * GT_LD + lane;
+        const float ig = accurate_sigmoid(gr[0] + gpre[e][0]);
+        const float fg = accurate_sigmoid(gr[32] + gpre[e][1]);
+        const float gg = tanhf(gr[64] + gpre[e][2]);
+        const float og = accurate_sigmoid(gr[96] + gpre[e][3]);
+        const float cn = fg * cst[e] + ig * gg;
+        const float hn = og * tanhf(cn);
+        cst[e] = cn;
+        float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
+        go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
+        p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
+        p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
+        if (p.head_in && (s % p.repeat) == p.repeat - 1)
+          p.head_in[((size_t)t * B + b) * H + ug] = tanhf(hn);
+        split_bf16(hn, hi, lo);
+      }
+      const int off = ((lane >> 3) * NB + n) * 16 + (lane & 7) * 2;  // [chunk][n][8]
+      *reinterpret_cast<__nv_bfloat16*>(hs_buf + off) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(hs_buf + SM::HSTAGE_PLANE + off) = lo;
+    }
+    tc::fence_proxy_async_smem();
+    __syncthreads();
+
+    // ---- all-gather of h_s: one bulk copy per (destination CTA, plane), completing on the destination's barrier
+    if (s + 1 < S && tid < 2 * C) {
+      const uint32_t d = tid >> 1, plane = tid & 1;
+      const uint32_t src = tc::smem_u32(hs_buf + plane * SM::HSTAGE_PLANE);
+      const uint32_t dst_local = hb_addr + (nxt * 2 + plane) * SM::HB_PLANE + (4 * rank) * NB * 16;
+      tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, SM::HSTAGE_PLANE, tc::mapa(tc::smem_u32(&h_full[nxt]), d));
+    }
+  }
+  tc::fence_before_thread_sync();
+  cluster.sync();
+  if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, 32 > NB ? 32 : NB); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <int H, int NB>
+struct TcBwdSmem {
+  static constexpr int C = H / 32;
+  static constexpr int MT = (H + 127) / 128;                      // M tiles of 128 output units (rows >= H are zero)
+  static constexpr int MROWS = MT * 128;
+  static constexpr int A_PLANE = 16 * MROWS * 16;                 // [k-chunk 0..15][row j][8 bf16], K = 128 gate rows
+  static constexpr int DG_PLANE = 16 * NB * 16;                   // [k-chunk][n][8 bf16]
+  static constexpr int PS_SLOT = NB * 32 * 4;                     // fp32 [n][32 units] from one source CTA
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_DG = 2 * A_PLANE;                      // [plane]
+  static constexpr int OFF_PS = OFF_DG + 2 * DG_PLANE;            // [buf][src][n][32]
+  static constexpr int OFF_PSTAGE = OFF_PS + 2 * C * PS_SLOT;     // [dbuf][owner][n][32]
+  static constexpr int OFF_BAR = OFF_PSTAGE + 2 * C * PS_SLOT;
+  static constexpr int BYTES = OFF_BAR + 64;
+  static constexpr int TMEM_COLS = (MT * NB) < 32 ? 32 : (MT * NB);
+  static_assert(BYTES <= 232448, "backward scan tile does not fit in 227 KB of shared memory");
+};
+
+template <int H, int NB>
+__global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwdParams p, int* err) {
+  using SM = TcBwdSmem<H, NB>;
+  constexpr int C = SM::C, MT = SM::MT, MROWS = SM::MROWS, NT = NB / 8;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / C) * NB;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int B = p.B, S = p.T * p.repeat;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* a_hi = smem + SM::OFF_A;
+  unsigned char* a_lo = a_hi + SM::A_PLANE;
+  unsigned char* dgs = smem + SM::OFF_DG;
+  float* ps = reinterpret_cast<float*>(smem + SM::OFF_PS);
+  float* pstage = reinterpret_cast<float*>(smem + SM::OFF_PSTAGE);
+  uint64_t* ps_full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);  // [2]
+  uint64_t* mma_done = ps_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  if (tid == 0) {
+    tc::mbar_init(&ps_full[0], 1);
+    tc::mbar_init(&ps_full[1], 1);
+    tc::mbar_init(mma_done, 1);
+    tc::fence_mbar_init_cluster();
+    *dead = 0;
+  }
+  if (w == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, SM::TMEM_COLS); }
+
+  // ---- A(j, r) = W_hh[grow(r)][j]: rows j = output units (all H), K index r = local gate row (gate*32 + unit)
+  for (int idx = tid; idx < MROWS * 16; idx += TC_THREADS) {
+    const int j = idx % MROWS, kc = idx / MROWS;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = kc * 8 + i;
+      v[i] = (j < H) ? __ldg(p.whh + (size_t)((r >> 5) * H + rank * 32 + (r & 31)) * H + j) : 0.f;
+    }
+    split8_store(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]),
+                 a_hi + kc * MROWS * 16 + j * 16, a_lo + kc * MROWS * 16 + j * 16);
+  }
+  const int ug = rank * 32 + lane;
+  const size_t gstride = (size_t)4 * H;
+  float dcn[NT], keep[NT][4];
+#pragma unroll
+  for (int e = 0; e < NT; ++e) {
+    dcn[e] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) keep[e][q] = 0.f;
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster.sync();
+
+  const uint32_t idesc = tc::make_idesc_bf16_f32(128, NB);
+  const uint32_t a_hi_addr = tc::smem_u32(a_hi), a_lo_addr = tc::smem_u32(a_lo), dg_addr = tc::smem_u32(dgs);
+  constexpr uint32_t STEP_TX = (uint32_t)C * (uint32_t)SM::PS_SLOT;
+
+  for (int it = 0; it < S; ++it) {
+    const int s = S - 1 - it;
+    const int buf = it & 1;
+    const int t = s / p.repeat;
+    const int rel = s - p.head_first_step;
+    const bool has_head = p.dh_head && rel >= 0 && (rel % p.repeat) == p.repeat - 1;
+
+    // prefetch the saved activations of this step before waiting for the partial sums
+    float pg[NT][4], pc_prev[NT], pc_new[NT], phead[NT];
+#pragma unroll
+    for (int e = 0; e < NT; ++e) {
+      const int b = b0 + w + 8 * e;
+      pc_prev[e] = pc_new[e] = phead[e] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pg[e][q] = 0.f;
+      if (b < B) {
+        const float* gs = p.gates + ((size_t)s * B + b) * gstride + ug;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pg[e][q] = gs[q * H];
+        pc_prev[e] = __ldg(p.cs + ((size_t)s * B + b) * H + ug);
+        pc_new[e] = __ldg(p.cs + ((size_t)(s + 1) * B + b) * H + ug);
+        if (has_head) phead[e] = __ldg(p.dh_head + ((size_t)(rel / p.repeat) * B + b) * H + ug);
+      }
+    }
+    if (it > 0 && !*dead) {
+      if (!tc::mbar_wait(&ps_full[buf], ((it - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 3); }
+    }
+
+    // ---- pointwise backward of the cell (thread = (unit = lane, n = w + 8e))
+#pragma unroll
+    for (int e = 0; e < NT; ++e) {
+      const int n = w + 8 * e, b = b0 + n;
+      float dg[4] = {0.f, 0.f, 0.f, 0.f};
+      if (b < B) {
+        float dh = phead[e];
+        if (it > 0) {
+#pragma unroll
+          for (int src = 0; src < C; ++src) dh += ps[((buf * C + src) * NB + n) * 32 + lane];
+        }
+        const float ig = pg[e][0], fg = pg[e][1], gg = pg[e][2], og = pg[e][3];
+        const float tcn = tanhf(pc_new[e]);
+        const float dc = dcn[e] + dh * og * (1.f - tcn * tcn);
+        dg[3] = dh * tcn * og * (1.f - og);
+        dg[0] = dc * gg * ig * (1.f - ig);
+        dg[1] = dc * pc_prev[e] * fg * (1.f - fg);
+        dg[2] = dc * ig * (1.f - gg * gg);
+        dcn[e] = dc * fg;
+        float* go = p.dgates + ((size_t)s * B + b) * gstride + ug;
+        go[0] = dg[0]; go[H] = dg[1]; go[2 * H] = dg[2]; go[3 * H] = dg[3];
+        if (p.repeat > 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) keep[e][q] += dg[q];
+          if (s % p.repeat == 0) {
+            float* gi = p.dgin + ((size_t)t * B + b) * gstride + ug;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { gi[q * H] = keep[e][q]; keep[e][q] = 0.f; }
+          }
+        }
+      }
+      // operand tile of the MMA: K index r = q*32 + lane -> chunk (q*4 + lane/8), element lane%8
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(dg[q], hi, lo);
+        const int off = ((q * 4 + (lane >> 3)) * NB + n) * 16 + (lane & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(dgs + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(dgs + SM::DG_PLANE + off) = lo;
+      }
+    }
+    if (s == 0) break;  // dh_{-1} is not needed: the initial state is data, not a parameter
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+
+    if (tid == 0) {
+      tc::mbar_arrive_expect_tx(&ps_full[buf ^ 1], STEP_TX);
+      tc::fence_after_thread_sync();
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t da_hi = tc::make_smem_desc(a_hi_addr + ks * 2 * MROWS * 16 + mt * 2048, MROWS * 16, 128);
+          const uint64_t da_lo = tc::make_smem_desc(a_lo_addr + ks * 2 * MROWS * 16 + mt * 2048, MROWS * 16, 128);
+          const uint64_t db_hi = tc::make_smem_desc(dg_addr + ks * 2 * NB * 16, NB * 16, 128);
+          const uint64_t db_lo = tc::make_smem_desc(dg_addr + SM::DG_PLANE + ks * 2 * NB * 16, NB * 16, 128);
+          const uint32_t d = tmem_base + mt * NB;
+          tc::mma_bf16_ss(d, da_lo, db_hi, idesc, ks > 0);
+          tc::mma_bf16_ss(d, da_hi, db_lo, idesc, true);
+          tc::mma_bf16_ss(d, da_hi, db_hi, idesc, true);
+        }
+      }
+      tc::mma_commit(mma_done);
+    }
+    if (!*dead) {
+      if (!tc::mbar_wait(mma_done, it & 1)) { *dead = 1; atomicExch(err, 4); }
+    }
+    tc::fence_after_thread_sync();
+    __syncwarp();
+
+    // ---- partial sums -> staging [owner CTA][n][32 units]; lane = output unit j within the 128-row tile
+    float* pst = pstage + (size_t)(it & 1) * C * NB * 32;
+    {
+      const int q = w & 3, ch = w >> 2;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int j = mt * 128 + q * 32 + lane;
+#pragma unroll
+        for (int part = 0; part < NB / 16; ++part) {
+          const int c0 = ch * (NB / 2) + part * 8;
+          float v[8];
+          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB + c0), v);
+          if (j < H) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pst[(((j >> 5) * NB) + c0 + i) * 32 + (j & 31)] = v[i];
+          }
+        }
+      }
+    }
+    tc::fence_before_thread_sync();
+    tc::fence_proxy_async_smem();
+    __syncthreads();
+    if (tid < C) {  // reduce-scatter: my partials for owner `tid`'s units -> its slot [buf^1][my rank]
+      const uint32_t d = tid;
+      const uint32_t src = tc::smem_u32(pst + (size_t)d * NB * 32);
+      const uint32_t dst_local = tc::smem_u32(ps + ((size_t)((buf ^ 1) * C + rank) * NB) * 32);
+      tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, SM::PS_SLOT, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
+    }
+  }
+  tc::fence_before_thread_sync();
+  cluster.sync();
+  if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, SM::TMEM_COLS); }
+}
+
+template <typename Kern, typename Params>
+int launch_cluster_tc(Kern kern, const Params& p, int cluster_size, int n_clusters, int smem_bytes, cudaStream_t stream) {
+  R2D2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster_size * n_clusters);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int* err = scan_error_flag();
+  R2D2_REQUIRE(err != nullptr, "scan error flag allocation failed");
+  R2D2_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, err));
+  count_launch();
+  return R2D2_OK;
+}
+
+int pick_nb_tc(int B, int H) {
+  const int avail = 148 / (H / 32);
+  return (ceil_div(B, 16) <= avail) ? 16 : 32;
+}
+
+template <int H>
+int fwd_tc(const ScanFwdParams& p, cudaStream_t stream) {
+  if (pick_nb_tc(p.B, H) == 16)
+    return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 16>, p, H / 32, ceil_div(p.B, 16), TcFwdSmem<H, 16>::BYTES, stream);
+  return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 32>, p, H / 32, ceil_div(p.B, 32), TcFwdSmem<H, 32>::BYTES, stream);
+}
+template <int H>
+int bwd_tc(const ScanBwdParams& p, cudaStream_t stream) {
+  // NB = 16 only: the double-buffered fp32 partial-sum slots of an NB = 32 tile do not fit next to the 128 KB W slice
+  return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 16>, p, H / 32, ceil_div(p.B, 16), TcBwdSmem<H, 16>::BYTES, stream);
+}
+
+}  // namespace
+
+int* scan_error_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+int lstm_scan_error_status(int* out, cudaStream_t stream) {
+  int* flag = scan_error_flag();
+  R2D2_REQUIRE(flag && out, "flag");
+  R2D2_CUDA_TRY(cudaMemcpyAsync(out, flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  R2D2_CUDA_TRY(cudaStreamSynchronize(stream));
+  return R2D2_OK;
+}
+
+int lstm_scan_forward_tc(const ScanFwdParams& p, cudaStream_t stream) {
+  switch (p.H) {
+    case 32: return fwd_tc<32>(p, stream);
+    case 64: return fwd_tc<64>(p, stream);
+    case 128: return fwd_tc<128>(p, stream);
+    case 256: return fwd_tc<256>(p, stream);
+    default: break;
+  }
+  set_last_error("tcgen05 scan: unsupported hidden size");
+  return R2D2_ERR_UNSUPPORTED;
+}
+
+int lstm_scan_backward_tc(const ScanBwdParams& p, cudaStream_t stream) {
+  switch (p.H) {
+    case 32: return bwd_tc<32>(p, stream);
+    case 64: return bwd_tc<64>(p, stream);
+    case 128: return bwd_tc<128>(p, stream);
+    case 256: return bwd_tc<256>(p, stream);
+    default: break;
+  }
+  set_last_error("tcgen05 scan: unsupported hidden size");
+  return R2D2_ERR_UNSUPPORTED;
+}
+
+}  // namespace r2d2

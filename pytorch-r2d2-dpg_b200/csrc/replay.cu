@@ -316,6 +316,7 @@ int replay_stats(Replay* r, r2d2_replay_stats_t* out, cudaStream_t stream) {
   long long nodes = 0;
   for (int l = 0; l < r->tv.levels; ++l) nodes += r->tv.n[l];
   out->tree_nodes = nodes;
+  out->last_row_start = r->episodes.empty() ? -1 : r->episodes.back().row_start;
   out->total_priority = total;
   return R2D2_OK;
 }

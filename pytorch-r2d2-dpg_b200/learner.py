@@ -1,0 +1,110 @@
+"""Drop-in for the reference's learner.py: `Learner(n_actors)`, `.run()`, `.save_model()`,
+`.update_target_model()`, `learner_process(n_actors)` (learner.py:18-67) with the same attributes,
+hyper-parameter literals, cwd-relative ./model_data and ./memory_data protocol and checkpoint keys -
+so the reference's r2d2.py launcher runs unchanged - while every iteration of the loop body
+(learner.py:84-139) executes in libr2d2_b200 (hand-written sm_100a CUDA):
+
+    memory.sample()          -> DeviceReplay.sample_into   (sum-tree draw + gather kernels, HBM resident)
+    burn-in / unrolls / BPTT -> LearnerEngine.step         (persistent cluster LSTM scans + tensor-core GEMMs)
+    target, loss, priorities -> fused TD/priority kernel, written back into the sum tree on device
+
+With torch.distributed initialised (one process per GPU) each rank owns its replay shard and the two
+flat gradient buffers are all-reduced over NCCL at the optimiser steps; nothing else crosses GPUs.
+"""
+import os
+from time import sleep, time
+
+import numpy as np
+import torch
+
+from replay_memory import LearnerReplayMemory
+from utils import get_obs
+
+WALKER_OBS, WALKER_ACT = 24, 6  # dm_control walker/run (learner.py:24-26), used when dm_control is absent
+
+
+def _env_sizes():
+    """(obs_size, n_actions).  The reference builds a dm_control env only to read these (learner.py:24-26)."""
+    if "R2D2_OBS_SIZE" in os.environ:
+        return int(os.environ["R2D2_OBS_SIZE"]), int(os.environ["R2D2_N_ACTIONS"])
+    try:
+        from dm_control import suite
+        env = suite.load(domain_name="walker", task_name="run")
+        return get_obs(env.reset().observation).shape[1], env.action_spec().shape[0]
+    except ImportError:
+        return WALKER_OBS, WALKER_ACT
+
+
+def learner_process(n_actors):
+    learner = Learner(n_actors)
+    learner.run()
+
+
+class Learner:
+    def __init__(self, n_actors, hidden=None, batch_size=None, device=None):
+        from r2d2_b200.engine import LearnerEngine, PathConfig
+        self.obs_size, self.n_actions = _env_sizes()
+        self.n_actors = n_actors
+        self.burn_in_length = 20
+        self.learning_length = 40
+        self.sequence_length = self.burn_in_length + self.learning_length
+        self.n_step = 5
+        self.memory_sequence_size = 5000000
+        self.batch_size = batch_size or int(os.environ.get("R2D2_BATCH", 32))
+        self.hidden = hidden or int(os.environ.get("R2D2_HIDDEN", 128))
+        self.model_path = './model_data/'
+        self.memory_path = './memory_data/'
+        self.model_save_interval = 50
+        self.memory_update_interval = 50
+        self.target_update_inverval = 500
+        self.gamma, self.actor_lr, self.critic_lr = 0.997, 1e-4, 1e-3
+        cfg = PathConfig(obs=self.obs_size, act=self.n_actions, hidden=self.hidden, batch=self.batch_size,
+                         burn_in=self.burn_in_length, learning=self.learning_length, n_step=self.n_step,
+                         gamma=self.gamma, actor_lr=self.actor_lr, critic_lr=self.critic_lr,
+                         target_interval=self.target_update_inverval)
+        self.engine = LearnerEngine(cfg, device=device)
+        self.engine.enable_data_parallel()
+        self.memory = LearnerReplayMemory(memory_sequence_size=self.memory_sequence_size, batch_size=self.batch_size,
+                                          obs_size=self.obs_size, n_actions=self.n_actions, hidden=self.hidden,
+                                          device=self.engine.device)
+        self.save_model()
+
+    # the four nets as state_dict-compatible views of the engine's flat parameter blocks
+    def _sd(self, net):
+        return {k: v.detach().clone() for k, v in self.engine.views(net).items()}
+
+    def save_model(self):
+        """model.pt = {'actor','target_actor','critic','target_critic'} state_dicts (learner.py:56-61)."""
+        model_dict = {net: self._sd(net) for net in ('actor', 'target_actor', 'critic', 'target_critic')}
+        tmp = self.model_path + 'model.pt.tmp{}'.format(os.getpid())
+        torch.save(model_dict, tmp)
+        os.replace(tmp, self.model_path + 'model.pt')
+
+    def update_target_model(self):
+        self.engine.flat['target_actor'].copy_(self.engine.flat['actor'])
+        self.engine.flat['target_critic'].copy_(self.engine.flat['critic'])
+
+    def _ingest(self):
+        for i in range(self.n_actors):
+            if os.path.isfile(self.memory_path + '/memory{}.pt'.format(i)):
+                self.memory.load(i)
+
+    def run(self, max_steps=None):
+        while self.memory.sequence_counter < self.batch_size * 100:   # warm-up gate, learner.py:69-75
+            self._ingest()
+            sleep(0.1)
+            print('learner memory sequence size:', self.memory.sequence_counter)
+        step = 0
+        dev = self.memory._dev
+        while max_steps is None or step < max_steps:
+            if step % 100 == 0:
+                print('learning step:', step)
+            step += 1
+            dev.sample_into(self.engine)                               # learner.py:84
+            self.engine.step()                                         # learner.py:86-132
+            dev.update_priorities(self.engine.leaf_idx, self.engine.priority)   # learner.py:135-139
+            if step % self.model_save_interval == 0:
+                self.save_model()
+            if step % self.memory_update_interval == 0:
+                self._ingest()                                         # learner.py:144-149 without the sleep stall
+        torch.cuda.synchronize()

@@ -37,7 +37,7 @@ class ReplayConfig(Structure):
 class ReplayStats(Structure):
     _fields_ = [("n_episodes", c_longlong), ("n_rows_used", c_longlong), ("sequence_counter", c_longlong),
                 ("capacity_rows", c_longlong), ("tree_levels", c_longlong), ("tree_nodes", c_longlong),
-                ("total_priority", c_double)]
+                ("last_row_start", c_longlong), ("total_priority", c_double)]
 
 
 class LearnerConfig(Structure):
@@ -75,6 +75,9 @@ SIGNATURES = {
                                        c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "r2d2_lstm_scan_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                         c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "r2d2_set_scan_impl": (c_int, [c_int]),
+    "r2d2_get_scan_impl": (c_int, []),
+    "r2d2_scan_status": (c_int, [POINTER(c_int), c_void_p]),
     "r2d2_td_priority": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                  c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r2d2_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_float, c_float,

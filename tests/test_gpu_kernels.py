@@ -118,8 +118,21 @@ NET_CASES = [
 ]
 
 
+@pytest.fixture(params=["tc", "mma"])
+def scan_impl(request, nv):
+    """Run the chain tests on both scan implementations: tcgen05/TMEM (default) and the mma.sync v1 kernels."""
+    lib = nv.lib()
+    lib.r2d2_set_scan_impl(1 if request.param == "tc" else 0)
+    yield request.param
+    import ctypes
+    status = ctypes.c_int(0)
+    nv.check(lib.r2d2_scan_status(ctypes.byref(status), nv.current_stream()))
+    lib.r2d2_set_scan_impl(1)
+    assert status.value == 0, f"a bounded mbarrier wait timed out inside a scan kernel (code {status.value})"
+
+
 @pytest.mark.parametrize("O,A,H,B,T,repeat,critic,first_row", NET_CASES)
-def test_net_forward_backward(nv, O, A, H, B, T, repeat, critic, first_row):
+def test_net_forward_backward(nv, scan_impl, O, A, H, B, T, repeat, critic, first_row):
     rng = np.random.default_rng(O * 1000 + H + B)
     p = make_params(rng, O, A, H, critic)
     obs = rng.standard_normal((T, B, O))
