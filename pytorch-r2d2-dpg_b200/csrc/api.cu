@@ -112,6 +112,13 @@ int r2d2_lstm_scan_backward(const float* gates, const float* hs, const float* cs
   return lstm_scan_backward(p, S(stream));
 }
 
+int r2d2_debug_scan_forward_trace(const float* gin, const float* whh, float* gates, float* hs, float* cs, int T, int B,
+                                  int H, long long* trace, r2d2_stream_t stream) {
+  ScanFwdParams p;
+  p.gin = gin; p.whh = whh; p.gates = gates; p.hs = hs; p.cs = cs; p.T = T; p.B = B; p.H = H; p.repeat = 1; p.trace = trace;
+  return lstm_scan_forward(p, S(stream));
+}
+
 int r2d2_set_scan_impl(int impl) { lstm_scan_set_impl(impl); return R2D2_OK; }
 int r2d2_get_scan_impl(void) { return lstm_scan_get_impl(); }
 int r2d2_scan_status(int* status, r2d2_stream_t stream) { return lstm_scan_error_status(status, S(stream)); }

@@ -18,6 +18,7 @@ struct ScanFwdParams {
   float* head_in = nullptr;     // optional [T,B,H]: tanh(h) at steps s % repeat == repeat-1 (actor head input)
   int T = 0, B = 0, H = 0, repeat = 1;   // S = T*repeat; repeat=2 reproduces the double actor step (learner.py:122-123)
   float* scratch = nullptr;     // generic path only: [B,4H]
+  long long* trace = nullptr;   // debug: [grid][S][8] globaltimer stamps written by thread 0 of every CTA (tcgen05 kernel)
 };
 
 struct ScanBwdParams {

@@ -29,7 +29,18 @@ namespace {
 constexpr int TC_THREADS = 256;
 constexpr int GT_LD = 128 + 4;
 
-__device__ __forceinline__ float accurate_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Cell non-linearities on the serial chain: exp via MUFU.EX2 (__expf, ~2 ulp) and an approximate reciprocal
+// (1 ulp); absolute error ~1e-7, far below the bf16x3 operand split (~1e-5) and the 1e-3 parity bar.  The
+// library versions (expf / tanhf / IEEE divide) cost ~0.85 us per step here: two dependent elements per thread.
+__device__ __forceinline__ float fast_sigmoid(float x) { return tc::sigmoid_fast(x); }
+__device__ __forceinline__ float fast_tanh(float x) { return tc::tanh_fast(x); }
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE_STAMP(slot) do { if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * S + s) * 8 + (slot)] = gtime(); } while (0)
 
 __device__ __forceinline__ void split8_store(const float4 v0, const float4 v1, unsigned char* hi_dst, unsigned char* lo_dst) {
   uint4 h, l;
@@ -44,10 +55,13 @@ __device__ __forceinline__ void split8_store(const float4 v0, const float4 v1, u
 template <int H, int NB>
 struct TcFwdSmem {
   static constexpr int C = H / 32, KC = H / 8;
-  static constexpr int A_PLANE = KC * 128 * 16;   // bytes: [k-chunk][row 0..127][8 bf16]
-  static constexpr int HB_PLANE = KC * NB * 16;   // bytes: [k-chunk][n][8 bf16]
-  static constexpr int OFF_A = 0;
-  static constexpr int OFF_HB = 2 * A_PLANE;                     // [buf][plane]
+  static constexpr int HB_PLANE = KC * NB * 16;   // bytes of one plane of the h operand (all H units, NB rows)
+  static constexpr int OFF_HB = 0;                               // [buf][rank slice][plane][4 chunks][NB][8 bf16]
+  // tensor memory columns: NACC independent accumulators D_a at [a*NB, ..) (a chain of dependent N=16 MMAs into ONE
+  // accumulator runs at the MMA pipeline latency, ~25 ns each, not at its throughput), then the W_hh slice: hi plane
+  // at 128 (H/2 columns: two bf16 per column), lo plane after it
+  static constexpr int NACC = (H / 16) < 4 ? (H / 16) : 4;
+  static constexpr int TM_A_HI = 128, TM_A_LO = 128 + H / 2, TM_COLS = 512;
   static constexpr int OFF_GT = OFF_HB + 4 * HB_PLANE;           // fp32 [NB][GT_LD]
   static constexpr int OFF_HSTAGE = OFF_GT + NB * GT_LD * 4;     // [dbuf][plane][4 chunks][NB][8] bf16
   static constexpr int HSTAGE_PLANE = 4 * NB * 16;               // bytes of one CTA's slice of one plane
@@ -64,11 +78,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
   const int rank = (int)cluster.block_rank();
   const int b0 = (blockIdx.x / C) * NB;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform warp index (role dispatch)
   const int B = p.B, S = p.T * p.repeat;
 
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* a_hi = smem + SM::OFF_A;
-  unsigned char* a_lo = a_hi + SM::A_PLANE;
   unsigned char* hb = smem + SM::OFF_HB;
   float* gt = reinterpret_cast<float*>(smem + SM::OFF_GT);
   unsigned char* hstage = smem + SM::OFF_HSTAGE;
@@ -84,16 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
     tc::fence_mbar_init_cluster();
     *dead = 0;
   }
-  if (w == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, 32 > NB ? 32 : NB); }
-
-  // ---- W_hh slice -> shared (bf16 hi/lo, UMMA K-major core matrices): row r = gate*32 + unit
-  for (int idx = tid; idx < 128 * KC; idx += TC_THREADS) {
-    const int r = idx & 127, kc = idx >> 7;
-    const float* src = p.whh + (size_t)((r >> 5) * H + rank * 32 + (r & 31)) * H + kc * 8;
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-    split8_store(v0, v1, a_hi + kc * 2048 + r * 16, a_lo + kc * 2048 + r * 16);
-  }
+  if (w == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, SM::TM_COLS); }
   // ---- initial h tile (all H units of my NB rows) -> operand buffer 0
   for (int idx = tid; idx < NB * KC; idx += TC_THREADS) {
     const int n = idx % NB, kc = idx / NB, b = b0 + n;
@@ -103,7 +107,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
       v0 = __ldg(reinterpret_cast<const float4*>(src));
       v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
     }
-    split8_store(v0, v1, hb + 0 * SM::HB_PLANE + kc * NB * 16 + n * 16, hb + 1 * SM::HB_PLANE + kc * NB * 16 + n * 16);
+    unsigned char* dst = hb + (kc >> 2) * 2 * SM::HSTAGE_PLANE + (kc & 3) * NB * 16 + n * 16;  // buffer 0
+    split8_store(v0, v1, dst, dst + SM::HSTAGE_PLANE);
   }
   const int ug = rank * 32 + lane;
   float cst[NT];
@@ -123,11 +128,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // ---- W_hh slice -> TENSOR MEMORY, resident for the whole launch: TMEM lane r = local gate row (gate = r/32 =
+  // lane quarter, unit = r%32), columns = K packed two bf16 per 32-bit word (hi plane, then lo plane).
+  {
+    const int q = w & 3, ch = w >> 2;
+    const float* wrow = p.whh + (size_t)(q * H + rank * 32 + lane) * H;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    __syncwarp();
+#pragma unroll 1
+    for (int ks = ch * (KS / 2); ks < (ch + 1) * (KS / 2); ++ks) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wrow + ks * 16 + i * 4));
+        split_pack2(v.x, v.y, hi[2 * i], lo[2 * i]);
+        split_pack2(v.z, v.w, hi[2 * i + 1], lo[2 * i + 1]);
+      }
+      tc::tmem_st_32x32b_x8(lane_base + SM::TM_A_HI + ks * 8, hi);
+      tc::tmem_st_32x32b_x8(lane_base + SM::TM_A_LO + ks * 8, lo);
+    }
+    tc::tmem_wait_st();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
   cluster.sync();  // every CTA's barriers are initialised before any remote copy can target them
 
   const uint32_t idesc = tc::make_idesc_bf16_f32(128, NB);
-  const uint32_t a_hi_addr = tc::smem_u32(a_hi), a_lo_addr = tc::smem_u32(a_lo), hb_addr = tc::smem_u32(hb);
+  const uint32_t hb_addr = tc::smem_u32(hb);
+  // the operand descriptor is loop invariant up to its 16-byte start-address field: build once, add offsets per k-step
+  const uint64_t db_hi0 = tc::make_smem_desc(hb_addr, NB * 16, 128);   // buffer 0, slice 0, plane hi
   const size_t gstride = (size_t)4 * H;
   constexpr uint32_t STEP_TX = (uint32_t)C * 2u * (uint32_t)SM::HSTAGE_PLANE;
 
@@ -144,28 +175,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
         gpre[e][q] = (b < B) ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;  // plain load: gates may alias gin
     }
 
-    if (tid == 0) {
-      if (s + 1 < S) tc::mbar_arrive_expect_tx(&h_full[nxt], STEP_TX);  // h_s from all C CTAs lands in buffer nxt
+    TRACE_STAMP(0);
+    if (w_u == 0) {  // MMA warp (warp-uniform branch); one elected lane issues
+      if (s + 1 < S && tc::elect_one()) tc::mbar_arrive_expect_tx(&h_full[nxt], STEP_TX);  // h_s of all C CTAs -> buffer nxt
       if (s > 0 && !*dead) {
         if (!tc::mbar_wait(&h_full[cur], ((s - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 1); }
       }
+      __syncwarp();
+      TRACE_STAMP(1);
       tc::fence_after_thread_sync();
-      const uint32_t hb_hi = hb_addr + (cur * 2 + 0) * SM::HB_PLANE, hb_lo = hb_addr + (cur * 2 + 1) * SM::HB_PLANE;
+      const uint64_t db_cur = db_hi0 + (uint64_t)((cur * 2 * SM::HB_PLANE) >> 4);
+      if (tc::elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        const uint64_t da_hi = tc::make_smem_desc(a_hi_addr + ks * 4096, 2048, 128);
-        const uint64_t da_lo = tc::make_smem_desc(a_lo_addr + ks * 4096, 2048, 128);
-        const uint64_t db_hi = tc::make_smem_desc(hb_hi + ks * 2 * NB * 16, NB * 16, 128);
-        const uint64_t db_lo = tc::make_smem_desc(hb_lo + ks * 2 * NB * 16, NB * 16, 128);
-        tc::mma_bf16_ss(tmem_base, da_lo, db_hi, idesc, ks > 0);
-        tc::mma_bf16_ss(tmem_base, da_hi, db_lo, idesc, true);
-        tc::mma_bf16_ss(tmem_base, da_hi, db_hi, idesc, true);
+        const uint32_t ta_hi = tmem_base + SM::TM_A_HI + ks * 8, ta_lo = tmem_base + SM::TM_A_LO + ks * 8;
+        const uint64_t db_hi = db_cur + (uint64_t)(((ks >> 1) * 2 * SM::HSTAGE_PLANE + (ks & 1) * 2 * NB * 16) >> 4);
+        const uint64_t db_lo = db_hi + (uint64_t)(SM::HSTAGE_PLANE >> 4);
+        const uint32_t d = tmem_base + (ks % SM::NACC) * NB;
+        tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks >= SM::NACC);
+        tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
+        tc::mma_bf16_ts(d, ta_hi, db_hi, idesc, true);
       }
       tc::mma_commit(mma_done);
+      }
+      __syncwarp();
+      TRACE_STAMP(2);
     }
     if (!*dead) {
       if (!tc::mbar_wait(mma_done, s & 1)) { *dead = 1; atomicExch(err, 2); }
     }
+    TRACE_STAMP(3);
     tc::fence_after_thread_sync();
     __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the spin wait
 
@@ -178,11 +217,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
         float v[8];
         tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
+        for (int a = 1; a < SM::NACC; ++a) {
+          float u[8];
+          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NB + c0), u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += u[j];
+        }
+#pragma unroll
         for (int j = 0; j < 8; ++j) gt[(c0 + j) * GT_LD + q * 32 + lane] = v[j];
       }
     }
     tc::fence_before_thread_sync();
     __syncthreads();
+    TRACE_STAMP(4);
 
     // ---- pointwise LSTM cell: thread = (unit = lane, batch column n = w + 8e); coalesced along units
     unsigned char* hs_buf = hstage + (s & 1) * 2 * SM::HSTAGE_PLANE;
@@ -192,39 +239,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
       __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
       if (b < B) {
         const float* gr = gt + n * GT_LD + lane;
-        const float ig = accurate_sigmoid(gr[0] + gpre[e][0]);
-        const float fg = accurate_sigmoid(gr[32] + gpre[e][1]);
-        const float gg = tanhf(gr[64] + gpre[e][2]);
-        const float og = accurate_sigmoid(gr[96] + gpre[e][3]);
+        const float ig = fast_sigmoid(gr[0] + gpre[e][0]);
+        const float fg = fast_sigmoid(gr[32] + gpre[e][1]);
+        const float gg = fast_tanh(gr[64] + gpre[e][2]);
+        const float og = fast_sigmoid(gr[96] + gpre[e][3]);
         const float cn = fg * cst[e] + ig * gg;
-        const float hn = og * tanhf(cn);
+        const float hn = og * fast_tanh(cn);
         cst[e] = cn;
         float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
         go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
         p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
         p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
         if (p.head_in && (s % p.repeat) == p.repeat - 1)
-          p.head_in[((size_t)t * B + b) * H + ug] = tanhf(hn);
+          p.head_in[((size_t)t * B + b) * H + ug] = fast_tanh(hn);
         split_bf16(hn, hi, lo);
       }
       const int off = ((lane >> 3) * NB + n) * 16 + (lane & 7) * 2;  // [chunk][n][8]
       *reinterpret_cast<__nv_bfloat16*>(hs_buf + off) = hi;
       *reinterpret_cast<__nv_bfloat16*>(hs_buf + SM::HSTAGE_PLANE + off) = lo;
     }
+    TRACE_STAMP(5);
     tc::fence_proxy_async_smem();
     __syncthreads();
+    TRACE_STAMP(6);
 
-    // ---- all-gather of h_s: one bulk copy per (destination CTA, plane), completing on the destination's barrier
-    if (s + 1 < S && tid < 2 * C) {
-      const uint32_t d = tid >> 1, plane = tid & 1;
-      const uint32_t src = tc::smem_u32(hs_buf + plane * SM::HSTAGE_PLANE);
-      const uint32_t dst_local = hb_addr + (nxt * 2 + plane) * SM::HB_PLANE + (4 * rank) * NB * 16;
-      tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, SM::HSTAGE_PLANE, tc::mapa(tc::smem_u32(&h_full[nxt]), d));
+    // ---- all-gather of h_s: one bulk copy (hi+lo planes, contiguous) per destination CTA, issued by lane 0 of
+    // warp d so the C copies leave from different schedulers; each completes on the destination's barrier
+    if (s + 1 < S && w_u < C && tc::elect_one()) {
+      const uint32_t d = w_u;
+      const uint32_t dst_local = hb_addr + nxt * 2 * SM::HB_PLANE + rank * 2 * SM::HSTAGE_PLANE;
+      tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf), 2 * SM::HSTAGE_PLANE,
+                               tc::mapa(tc::smem_u32(&h_full[nxt]), d));
     }
+    TRACE_STAMP(7);
   }
   tc::fence_before_thread_sync();
   cluster.sync();
-  if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, 32 > NB ? 32 : NB); }
+  if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, SM::TM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,33 +285,33 @@ template <int H, int NB>
 struct TcBwdSmem {
   static constexpr int C = H / 32;
   static constexpr int MT = (H + 127) / 128;                      // M tiles of 128 output units (rows >= H are zero)
-  static constexpr int MROWS = MT * 128;
-  static constexpr int A_PLANE = 16 * MROWS * 16;                 // [k-chunk 0..15][row j][8 bf16], K = 128 gate rows
   static constexpr int DG_PLANE = 16 * NB * 16;                   // [k-chunk][n][8 bf16]
   static constexpr int PS_SLOT = NB * 32 * 4;                     // fp32 [n][32 units] from one source CTA
-  static constexpr int OFF_A = 0;
-  static constexpr int OFF_DG = 2 * A_PLANE;                      // [plane]
+  static constexpr int OFF_DG = 0;                                // [plane]
+  // tensor memory: NACC independent accumulators per M tile, D_(mt,a) at [(mt*NACC + a)*NB, ..); W^T tiles from
+  // column 256: (mt, plane) -> 256 + (2 mt + plane) * 64
+  static constexpr int NACC = 4;
+  static constexpr int TM_A = 256, TM_COLS = 512;
+  static_assert(MT * NACC * NB <= 256, "accumulators overlap the weight tiles in tensor memory");
   static constexpr int OFF_PS = OFF_DG + 2 * DG_PLANE;            // [buf][src][n][32]
   static constexpr int OFF_PSTAGE = OFF_PS + 2 * C * PS_SLOT;     // [dbuf][owner][n][32]
   static constexpr int OFF_BAR = OFF_PSTAGE + 2 * C * PS_SLOT;
   static constexpr int BYTES = OFF_BAR + 64;
-  static constexpr int TMEM_COLS = (MT * NB) < 32 ? 32 : (MT * NB);
   static_assert(BYTES <= 232448, "backward scan tile does not fit in 227 KB of shared memory");
 };
 
 template <int H, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwdParams p, int* err) {
   using SM = TcBwdSmem<H, NB>;
-  constexpr int C = SM::C, MT = SM::MT, MROWS = SM::MROWS, NT = NB / 8;
+  constexpr int C = SM::C, MT = SM::MT, NT = NB / 8;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b0 = (blockIdx.x / C) * NB;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int B = p.B, S = p.T * p.repeat;
 
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* a_hi = smem + SM::OFF_A;
-  unsigned char* a_lo = a_hi + SM::A_PLANE;
   unsigned char* dgs = smem + SM::OFF_DG;
   float* ps = reinterpret_cast<float*>(smem + SM::OFF_PS);
   float* pstage = reinterpret_cast<float*>(smem + SM::OFF_PSTAGE);
@@ -276,20 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     tc::fence_mbar_init_cluster();
     *dead = 0;
   }
-  if (w == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, SM::TMEM_COLS); }
-
-  // ---- A(j, r) = W_hh[grow(r)][j]: rows j = output units (all H), K index r = local gate row (gate*32 + unit)
-  for (int idx = tid; idx < MROWS * 16; idx += TC_THREADS) {
-    const int j = idx % MROWS, kc = idx / MROWS;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = kc * 8 + i;
-      v[i] = (j < H) ? __ldg(p.whh + (size_t)((r >> 5) * H + rank * 32 + (r & 31)) * H + j) : 0.f;
-    }
-    split8_store(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]),
-                 a_hi + kc * MROWS * 16 + j * 16, a_lo + kc * MROWS * 16 + j * 16);
-  }
+  if (w == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, SM::TM_COLS); }
   const int ug = rank * 32 + lane;
   const size_t gstride = (size_t)4 * H;
   float dcn[NT], keep[NT][4];
@@ -303,11 +341,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // ---- A(j, r) = W_hh[grow(r)][j] -> TENSOR MEMORY: lane = output unit j within the 128-row tile mt, K index
+  // r = local gate row (gate*32 + unit) packed two per column; rows j >= H are zero
+  {
+    const int q = w & 3, ch = w >> 2;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    __syncwarp();
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int j = mt * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int ks = ch * 4; ks < ch * 4 + 4; ++ks) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = ks * 16 + 2 * i;
+          const size_t row0 = (size_t)((r >> 5) * H + rank * 32 + (r & 31));
+          const float v0 = (j < H) ? __ldg(p.whh + row0 * H + j) : 0.f;
+          const float v1 = (j < H) ? __ldg(p.whh + (row0 + 1) * H + j) : 0.f;
+          split_pack2(v0, v1, hi[i], lo[i]);
+        }
+        tc::tmem_st_32x32b_x8(lane_base + SM::TM_A + (2 * mt + 0) * 64 + ks * 8, hi);
+        tc::tmem_st_32x32b_x8(lane_base + SM::TM_A + (2 * mt + 1) * 64 + ks * 8, lo);
+      }
+    }
+    tc::tmem_wait_st();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
   cluster.sync();
 
   const uint32_t idesc = tc::make_idesc_bf16_f32(128, NB);
-  const uint32_t a_hi_addr = tc::smem_u32(a_hi), a_lo_addr = tc::smem_u32(a_lo), dg_addr = tc::smem_u32(dgs);
+  const uint64_t db_hi0 = tc::make_smem_desc(tc::smem_u32(dgs), NB * 16, 128);
   constexpr uint32_t STEP_TX = (uint32_t)C * (uint32_t)SM::PS_SLOT;
 
   for (int it = 0; it < S; ++it) {
@@ -350,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
           for (int src = 0; src < C; ++src) dh += ps[((buf * C + src) * NB + n) * 32 + lane];
         }
         const float ig = pg[e][0], fg = pg[e][1], gg = pg[e][2], og = pg[e][3];
-        const float tcn = tanhf(pc_new[e]);
+        const float tcn = fast_tanh(pc_new[e]);
         const float dc = dcn[e] + dh * og * (1.f - tcn * tcn);
         dg[3] = dh * tcn * og * (1.f - og);
         dg[0] = dc * gg * ig * (1.f - ig);
@@ -384,24 +451,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     tc::fence_before_thread_sync();
     __syncthreads();
 
-    if (tid == 0) {
-      tc::mbar_arrive_expect_tx(&ps_full[buf ^ 1], STEP_TX);
+    if (w_u == 0) {
       tc::fence_after_thread_sync();
+      if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(&ps_full[buf ^ 1], STEP_TX);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t da_hi = tc::make_smem_desc(a_hi_addr + ks * 2 * MROWS * 16 + mt * 2048, MROWS * 16, 128);
-          const uint64_t da_lo = tc::make_smem_desc(a_lo_addr + ks * 2 * MROWS * 16 + mt * 2048, MROWS * 16, 128);
-          const uint64_t db_hi = tc::make_smem_desc(dg_addr + ks * 2 * NB * 16, NB * 16, 128);
-          const uint64_t db_lo = tc::make_smem_desc(dg_addr + SM::DG_PLANE + ks * 2 * NB * 16, NB * 16, 128);
-          const uint32_t d = tmem_base + mt * NB;
-          tc::mma_bf16_ss(d, da_lo, db_hi, idesc, ks > 0);
-          tc::mma_bf16_ss(d, da_hi, db_lo, idesc, true);
-          tc::mma_bf16_ss(d, da_hi, db_hi, idesc, true);
+          const uint32_t ta_hi = tmem_base + SM::TM_A + (2 * mt + 0) * 64 + ks * 8;
+          const uint32_t ta_lo = tmem_base + SM::TM_A + (2 * mt + 1) * 64 + ks * 8;
+          const uint64_t db_hi = db_hi0 + (uint64_t)((ks * 2 * NB * 16) >> 4);
+          const uint64_t db_lo = db_hi + (uint64_t)(SM::DG_PLANE >> 4);
+          const uint32_t d = tmem_base + (mt * SM::NACC + (ks % SM::NACC)) * NB;
+          tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks >= SM::NACC);
+          tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
+          tc::mma_bf16_ts(d, ta_hi, db_hi, idesc, true);
         }
       }
       tc::mma_commit(mma_done);
+      }
+      __syncwarp();
     }
     if (!*dead) {
       if (!tc::mbar_wait(mma_done, it & 1)) { *dead = 1; atomicExch(err, 4); }
@@ -420,7 +490,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
         for (int part = 0; part < NB / 16; ++part) {
           const int c0 = ch * (NB / 2) + part * 8;
           float v[8];
-          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB + c0), v);
+          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * SM::NACC * NB + c0), v);
+#pragma unroll
+          for (int a = 1; a < SM::NACC; ++a) {
+            float u[8];
+            tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * SM::NACC + a) * NB + c0), u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += u[i];
+          }
           if (j < H) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) pst[(((j >> 5) * NB) + c0 + i) * 32 + (j & 31)] = v[i];
@@ -431,8 +508,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     tc::fence_before_thread_sync();
     tc::fence_proxy_async_smem();
     __syncthreads();
-    if (tid < C) {  // reduce-scatter: my partials for owner `tid`'s units -> its slot [buf^1][my rank]
-      const uint32_t d = tid;
+    if (w_u < C && tc::elect_one()) {  // reduce-scatter: my partials for owner w's units -> its slot [buf^1][my rank]
+      const uint32_t d = w_u;
       const uint32_t src = tc::smem_u32(pst + (size_t)d * NB * 32);
       const uint32_t dst_local = tc::smem_u32(ps + ((size_t)((buf ^ 1) * C + rank) * NB) * 32);
       tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, SM::PS_SLOT, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
@@ -440,7 +517,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   }
   tc::fence_before_thread_sync();
   cluster.sync();
-  if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, SM::TMEM_COLS); }
+  if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, SM::TM_COLS); }
 }
 
 template <typename Kern, typename Params>
@@ -478,8 +555,9 @@ int fwd_tc(const ScanFwdParams& p, cudaStream_t stream) {
 }
 template <int H>
 int bwd_tc(const ScanBwdParams& p, cudaStream_t stream) {
-  // NB = 16 only: the double-buffered fp32 partial-sum slots of an NB = 32 tile do not fit next to the 128 KB W slice
-  return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 16>, p, H / 32, ceil_div(p.B, 16), TcBwdSmem<H, 16>::BYTES, stream);
+  if (pick_nb_tc(p.B, H) == 16)
+    return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 16>, p, H / 32, ceil_div(p.B, 16), TcBwdSmem<H, 16>::BYTES, stream);
+  return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 32>, p, H / 32, ceil_div(p.B, 32), TcBwdSmem<H, 32>::BYTES, stream);
 }
 
 }  // namespace

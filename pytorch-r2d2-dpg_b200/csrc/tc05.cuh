@@ -43,6 +43,20 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// A operand from TENSOR MEMORY (M=128: row i in lane i, K=16 bf16 packed two per 32-bit column -> 8 columns),
+// B from shared memory.  Keeps a stationary operand (the recurrent weights) out of the shared-memory
+// read path: an SS-mode M=128 MMA re-reads its 4 KB A tile from shared memory every issue.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
 // make the mbarrier track completion of all tcgen05.mma issued so far by this thread
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -73,6 +87,36 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, float (&v)[8])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// registers -> TMEM: thread i of the warp writes lane (base_lane + i), columns c..c+7
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- approximate transcendentals for the cell non-linearities on the serial chain: one MUFU each
+// (ex2.approx: 2^-22 relative, rcp.approx: 1 ulp) instead of the branchy library versions.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.0f * rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)) - 1.0f; }
+
+// one lane of a CONVERGED warp; with a warp-uniform enclosing branch the compiler keeps descriptor / address
+// operands in uniform registers and emits the tcgen05 / bulk-copy instruction once (a thread-divergent
+// `if (tid == 0)` makes it wrap every UTCHMMA in an ELECT / BRA.U.ANY loop: ~45 cycles per MMA issued)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- mbarrier (shared::cta), transaction-count based completion

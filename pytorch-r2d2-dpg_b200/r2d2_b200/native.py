@@ -75,6 +75,8 @@ SIGNATURES = {
                                        c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "r2d2_lstm_scan_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                         c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "r2d2_debug_scan_forward_trace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                              c_void_p, c_void_p]),
     "r2d2_set_scan_impl": (c_int, [c_int]),
     "r2d2_get_scan_impl": (c_int, []),
     "r2d2_scan_status": (c_int, [POINTER(c_int), c_void_p]),

@@ -112,6 +112,7 @@ NET_CASES = [
     (17, 6, 256, 40, 10, 1, True, 5),
     (17, 6, 256, 24, 6, 2, False, 0),
     (17, 6, 256, 150, 5, 1, False, 2),      # several clusters, ragged last tile
+    (17, 6, 256, 300, 4, 1, True, 1),       # more rows than one wave of NB=16 clusters -> NB=32 tiles
     (3, 1, 128, 9, 6, 1, True, 0),          # Pendulum shape, A = 1
     (6, 2, 96, 5, 4, 1, True, 1),           # generic scan path (H not covered by the cluster kernels)
     (6, 2, 96, 5, 3, 2, False, 0),
