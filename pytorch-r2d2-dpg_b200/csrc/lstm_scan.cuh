@@ -18,6 +18,7 @@ struct ScanFwdParams {
   float* head_in = nullptr;     // optional [T,B,H]: tanh(h) at steps s % repeat == repeat-1 (actor head input)
   int T = 0, B = 0, H = 0, repeat = 1;   // S = T*repeat; repeat=2 reproduces the double actor step (learner.py:122-123)
   float* scratch = nullptr;     // generic path only: [B,4H]
+  int rows_per_cluster = 0;     // set by the tcgen05 dispatcher: batch rows owned by one cluster (<= its N tile)
   long long* trace = nullptr;   // debug: [grid][S][8] globaltimer stamps written by thread 0 of every CTA (tcgen05 kernel)
 };
 
@@ -33,6 +34,7 @@ struct ScanBwdParams {
   float* dgin = nullptr;           // [T,B,4H] sum over the `repeat` steps sharing an input row (== dgates if repeat==1)
   int T = 0, B = 0, H = 0, repeat = 1;
   float* scratch = nullptr;        // generic path only: [2,B,H] (dh_rec, dc)
+  int rows_per_cluster = 0;        // set by the tcgen05 dispatcher
 };
 
 // true when the persistent cluster kernels cover this hidden size (H in {32,64,128,256})
@@ -51,5 +53,6 @@ int lstm_scan_forward_tc(const ScanFwdParams& p, cudaStream_t stream);
 int lstm_scan_backward_tc(const ScanBwdParams& p, cudaStream_t stream);
 // nonzero if a bounded mbarrier wait of a tcgen05 scan kernel ever timed out (protocol bug); synchronises the stream
 int lstm_scan_error_status(int* out, cudaStream_t stream);
+int lstm_scan_max_active_clusters(int H, int nb, int backward);
 
 }  // namespace r2d2

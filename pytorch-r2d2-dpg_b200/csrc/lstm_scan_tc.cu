@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
   constexpr int C = SM::C, KC = SM::KC, KS = H / 16, NT = NB / 8;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int b0 = (blockIdx.x / C) * NB;
+  const int b0 = (blockIdx.x / C) * p.rows_per_cluster;  // this cluster's batch rows [b0, b_end), at most NB of them
+  const int b_end = min(p.B, b0 + p.rows_per_cluster);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform warp index (role dispatch)
   const int B = p.B, S = p.T * p.repeat;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
   for (int idx = tid; idx < NB * KC; idx += TC_THREADS) {
     const int n = idx % NB, kc = idx / NB, b = b0 + n;
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    if (b < B && p.h0) {
+    if (b < b_end && p.h0) {
       const float* src = p.h0 + (size_t)b * H + kc * 8;
       v0 = __ldg(reinterpret_cast<const float4*>(src));
       v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
   for (int e = 0; e < NT; ++e) {
     const int b = b0 + w + 8 * e;
     cst[e] = 0.f;
-    if (b < B) {
+    if (b < b_end) {
       const float hv = p.h0 ? __ldg(p.h0 + (size_t)b * H + ug) : 0.f;
       const float cv = p.c0 ? __ldg(p.c0 + (size_t)b * H + ug) : 0.f;
       p.hs[(size_t)b * H + ug] = hv;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
       const int b = b0 + w + 8 * e;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        gpre[e][q] = (b < B) ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;  // plain load: gates may alias gin
+        gpre[e][q] = (b < b_end) ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;  // plain load: gates may alias gin
     }
 
     TRACE_STAMP(0);
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
     for (int e = 0; e < NT; ++e) {
       const int n = w + 8 * e, b = b0 + n;
       __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
-      if (b < B) {
+      if (b < b_end) {
         const float* gr = gt + n * GT_LD + lane;
         const float ig = fast_sigmoid(gr[0] + gpre[e][0]);
         const float fg = fast_sigmoid(gr[32] + gpre[e][1]);
@@ -306,7 +307,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   constexpr int C = SM::C, MT = SM::MT, NT = NB / 8;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int b0 = (blockIdx.x / C) * NB;
+  const int b0 = (blockIdx.x / C) * p.rows_per_cluster;  // this cluster's batch rows [b0, b_end), at most NB of them
+  const int b_end = min(p.B, b0 + p.rows_per_cluster);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int B = p.B, S = p.T * p.repeat;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       pc_prev[e] = pc_new[e] = phead[e] = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) pg[e][q] = 0.f;
-      if (b < B) {
+      if (b < b_end) {
         const float* gs = p.gates + ((size_t)s * B + b) * gstride + ug;
 #pragma unroll
         for (int q = 0; q < 4; ++q) pg[e][q] = gs[q * H];
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     for (int e = 0; e < NT; ++e) {
       const int n = w + 8 * e, b = b0 + n;
       float dg[4] = {0.f, 0.f, 0.f, 0.f};
-      if (b < B) {
+      if (b < b_end) {
         float dh = phead[e];
         if (it > 0) {
 #pragma unroll
@@ -542,22 +544,64 @@ int launch_cluster_tc(Kern kern, const Params& p, int cluster_size, int n_cluste
   return R2D2_OK;
 }
 
-int pick_nb_tc(int B, int H) {
-  const int avail = 148 / (H / 32);
-  return (ceil_div(B, 16) <= avail) ? 16 : 32;
+// how many clusters of this kernel the device can keep resident at once (GPC geometry decides, not just SM count)
+template <typename Kern>
+int max_active_clusters(Kern kern, int cluster_size, int smem_bytes) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster_size * 64);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
+
+// Tiling of the batch over clusters.  The chain is a serial dependency, so every cluster must be RESIDENT at once
+// (a cluster that waits for a free GPC slot doubles the chain's latency): ask the driver how many clusters of this
+// kernel fit (15 clusters of 8 on a B200, not 148/8 = 18: clusters cannot straddle GPCs) and, when 16-row tiles
+// would need more than that, spread the rows evenly over the resident clusters with the 32-column MMA tile.
+struct Tiling { int nb, rows_per_cluster, n_clusters; };
+
+template <int H, typename K16, typename K32>
+Tiling pick_tiling(int B, K16 k16, int smem16, K32 k32, int smem32) {
+  static int max16 = -2, max32 = -2;
+  if (max16 == -2) max16 = max_active_clusters(k16, H / 32, smem16);
+  if (max32 == -2) max32 = max_active_clusters(k32, H / 32, smem32);
+  const int fit16 = max16 > 0 ? max16 : 148 / (H / 32), fit32 = max32 > 0 ? max32 : 148 / (H / 32);
+  if (ceil_div(B, 16) <= fit16) return {16, 16, ceil_div(B, 16)};
+  int n = fit32;
+  if (ceil_div(B, n) > 32) n = ceil_div(B, 32);  // more rows than one wave can hold: full 32-row tiles, several waves
+  const int rows = ceil_div(B, n);
+  return {32, rows, ceil_div(B, rows)};
 }
 
 template <int H>
-int fwd_tc(const ScanFwdParams& p, cudaStream_t stream) {
-  if (pick_nb_tc(p.B, H) == 16)
-    return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 16>, p, H / 32, ceil_div(p.B, 16), TcFwdSmem<H, 16>::BYTES, stream);
-  return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 32>, p, H / 32, ceil_div(p.B, 32), TcFwdSmem<H, 32>::BYTES, stream);
+int fwd_tc(const ScanFwdParams& p_in, cudaStream_t stream) {
+  ScanFwdParams p = p_in;
+  const Tiling t = pick_tiling<H>(p.B, lstm_scan_fwd_tc_kernel<H, 16>, TcFwdSmem<H, 16>::BYTES,
+                                  lstm_scan_fwd_tc_kernel<H, 32>, TcFwdSmem<H, 32>::BYTES);
+  p.rows_per_cluster = t.rows_per_cluster;
+  if (t.nb == 16)
+    return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 16>, p, H / 32, t.n_clusters, TcFwdSmem<H, 16>::BYTES, stream);
+  return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 32>, p, H / 32, t.n_clusters, TcFwdSmem<H, 32>::BYTES, stream);
 }
 template <int H>
-int bwd_tc(const ScanBwdParams& p, cudaStream_t stream) {
-  if (pick_nb_tc(p.B, H) == 16)
-    return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 16>, p, H / 32, ceil_div(p.B, 16), TcBwdSmem<H, 16>::BYTES, stream);
-  return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 32>, p, H / 32, ceil_div(p.B, 32), TcBwdSmem<H, 32>::BYTES, stream);
+int bwd_tc(const ScanBwdParams& p_in, cudaStream_t stream) {
+  ScanBwdParams p = p_in;
+  const Tiling t = pick_tiling<H>(p.B, lstm_scan_bwd_tc_kernel<H, 16>, TcBwdSmem<H, 16>::BYTES,
+                                  lstm_scan_bwd_tc_kernel<H, 32>, TcBwdSmem<H, 32>::BYTES);
+  p.rows_per_cluster = t.rows_per_cluster;
+  if (t.nb == 16)
+    return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 16>, p, H / 32, t.n_clusters, TcBwdSmem<H, 16>::BYTES, stream);
+  return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 32>, p, H / 32, t.n_clusters, TcBwdSmem<H, 32>::BYTES, stream);
 }
 
 }  // namespace
@@ -577,6 +621,16 @@ int lstm_scan_error_status(int* out, cudaStream_t stream) {
   R2D2_CUDA_TRY(cudaMemcpyAsync(out, flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
   R2D2_CUDA_TRY(cudaStreamSynchronize(stream));
   return R2D2_OK;
+}
+
+int lstm_scan_max_active_clusters(int H, int nb, int backward) {
+  if (H == 256 && nb == 16) return backward ? max_active_clusters(lstm_scan_bwd_tc_kernel<256, 16>, 8, TcBwdSmem<256, 16>::BYTES)
+                                           : max_active_clusters(lstm_scan_fwd_tc_kernel<256, 16>, 8, TcFwdSmem<256, 16>::BYTES);
+  if (H == 256 && nb == 32) return backward ? max_active_clusters(lstm_scan_bwd_tc_kernel<256, 32>, 8, TcBwdSmem<256, 32>::BYTES)
+                                           : max_active_clusters(lstm_scan_fwd_tc_kernel<256, 32>, 8, TcFwdSmem<256, 32>::BYTES);
+  if (H == 128 && nb == 16) return backward ? max_active_clusters(lstm_scan_bwd_tc_kernel<128, 16>, 4, TcBwdSmem<128, 16>::BYTES)
+                                           : max_active_clusters(lstm_scan_fwd_tc_kernel<128, 16>, 4, TcFwdSmem<128, 16>::BYTES);
+  return -1;
 }
 
 int lstm_scan_forward_tc(const ScanFwdParams& p, cudaStream_t stream) {
