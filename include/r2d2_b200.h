@@ -97,6 +97,9 @@ int r2d2_debug_scan_forward_trace(const float* gin, const float* whh, float* gat
                                   int H, long long* trace, r2d2_stream_t stream);
 /* debug: clusters of the tcgen05 scan kernel the device can keep resident at once (-1 if not instantiated) */
 int r2d2_debug_max_active_clusters(int H, int nb, int backward);
+/* GEMM implementation switch for A/B checks: 1 = tcgen05/TMEM (default), 0 = mma.sync v1 kernel */
+int r2d2_set_gemm_impl(int impl);
+int r2d2_get_gemm_impl(void);
 /* scan implementation switch for A/B checks: 1 = tcgen05/TMEM (default), 0 = mma.sync v1 kernels */
 int r2d2_set_scan_impl(int impl);
 int r2d2_get_scan_impl(void);

@@ -3,6 +3,8 @@
 // CTA tile 128x64x32, 8 warps (4 along M x 2 along N), register-staged double buffering.
 #include "gemm.cuh"
 
+#include <stdlib.h>
+
 namespace r2d2 {
 namespace {
 
@@ -241,7 +243,18 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+static int g_gemm_impl = -1;
+void gemm_set_impl(int impl) { g_gemm_impl = impl ? 1 : 0; }
+int gemm_get_impl() {
+  if (g_gemm_impl < 0) {
+    const char* e = getenv("R2D2_GEMM_IMPL");
+    g_gemm_impl = (e && (e[0] == 'm' || e[0] == '0')) ? 0 : 1;
+  }
+  return g_gemm_impl;
+}
+
 int gemm_suggest_split_k(int M, int N, int K) {
+  if (gemm_get_impl() == 1) return gemm_tc_suggest_split_k(M, N, K);
   long long tiles = (long long)ceil_div(M, BM) * ceil_div(N, BN);
   int k_tiles = ceil_div(K, BK);
   if (tiles >= 148 || k_tiles < 16) return 1;
@@ -262,6 +275,7 @@ int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   R2D2_REQUIRE(p.K2 == 0 || (p.A2 && p.B2), "segment 2 operands");
   R2D2_REQUIRE((p.epilogue != EPI_MUL_DTANH && p.epilogue != EPI_ADD_Z) || p.Z, "epilogue needs Z");
   R2D2_REQUIRE(ceil_div(p.M, BM) <= 65535, "M too large for grid.y");
+  if (gemm_get_impl() == 1) return gemm_f32_tc(p, layout, stream);
   switch (layout) {
     case GEMM_NT: return launch_gemm<GEMM_NT>(p, stream);
     case GEMM_NN: return launch_gemm<GEMM_NN>(p, stream);

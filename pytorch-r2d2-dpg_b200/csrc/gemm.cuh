@@ -38,4 +38,10 @@ int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream);
 // picks a split-K factor so that a skinny-output wgrad GEMM fills the 148 SMs
 int gemm_suggest_split_k(int M, int N, int K);
 
+// implementation: 1 = tcgen05/TMEM kernel (default), 0 = mma.sync v1 kernel; env R2D2_GEMM_IMPL = "tc" | "mma"
+void gemm_set_impl(int impl);
+int gemm_get_impl();
+int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream);
+int gemm_tc_suggest_split_k(int M, int N, int K);
+
 }  // namespace r2d2
