@@ -41,11 +41,24 @@ GEMM_CASES = [
     (2, 6, 256, 3000, 0, False, 0, 4),       # dW3
     (2, 256, 17, 4000, 0, False, 0, 5),      # dW1 obs block (ldb = 17)
     (0, 100, 64, 40, 0, False, 3, 1),        # add-Z epilogue (generic scan path)
+    (0, 4000, 1024, 256, 0, True, 0, 1),     # x*W_ih^T shape (many k tiles, full N tiles)
+    (1, 3000, 256, 1024, 0, False, 2, 1),
+    (2, 1024, 256, 30720, 0, False, 0, 16),  # dW_hh at cfg-2 size
+    (0, 130, 257, 77, 0, True, 1, 1),        # ragged everything
+    (1, 257, 130, 77, 0, False, 0, 1),
+    (2, 130, 257, 777, 0, False, 0, 3),
 ]
 
 
+@pytest.fixture(params=["tc", "mma"])
+def gemm_impl(request, nv):
+    nv.lib().r2d2_set_gemm_impl(1 if request.param == "tc" else 0)
+    yield request.param
+    nv.lib().r2d2_set_gemm_impl(1)
+
+
 @pytest.mark.parametrize("layout,M,N,K,K2,bias,epi,split", GEMM_CASES)
-def test_gemm(nv, layout, M, N, K, K2, bias, epi, split):
+def test_gemm(nv, gemm_impl, layout, M, N, K, K2, bias, epi, split):
     rng = np.random.default_rng(hash((layout, M, N, K)) % 2 ** 31)
     if layout == 0:
         A, Bm = rng.standard_normal((M, K)), rng.standard_normal((N, K + K2))
