@@ -21,9 +21,12 @@ constexpr int TC_GEMM_SMEM = TSTAGES * STAGE_BYTES + 128;
 constexpr int GROUPS = 128 * TBK / 8;               // 512 groups of 8 elements per operand tile
 
 // one group = 8 consecutive elements along the operand's contiguous global dimension -> one 16-byte smem row
-// of a core matrix.  smem byte offset of group `id` is id*16 for both majors (GEMM layouts):
-//   K-major  (global [row][k]):  row = id % 128, k = 8*(id/128) .. +8        core matrix = 8 rows x 16 B
-//   MN-major (global [k][mn]) :  k = 8*(id/128) + id%8, mn = 8*((id/8)%16) .. +8   core matrix = 8 k x 16 B
+// of a core matrix.  The smem byte offset of group `id` is id*16 for both majors, and a warp's 32 groups are
+// 8 global rows x 128 contiguous bytes (4 lanes share a cache line), written as 4 conflict-free 128-byte core matrices:
+//   K-major  (global [row][k]):  row = 8*(id/32) + id%8, k = 8*((id/8)%4) .. +8      smem [row/8][k/8][row%8][16 B]
+//                                 -> descriptor LBO (k-group stride) = 128, SBO (8-row-group stride) = 512
+//   MN-major (global [k][mn]) :  k = 8*(id/128) + id%8, mn = 8*((id/8)%16) .. +8     smem [k/8][mn/8][k%8][16 B]
+//                                 -> descriptor LBO (k-group stride) = 2048, SBO (8-mn-group stride) = 128
 struct OperandSrc {
   const float* ptr;
   long long ld;
@@ -40,7 +43,7 @@ __device__ __forceinline__ void load_group(const OperandSrc& o, int id, float4& 
   v1 = v0;
   int row, col, row_lim, col_lim;  // global [row][col], 8 consecutive cols
   if (MN_MAJOR) { row = o.k0 + 8 * (id >> 7) + (id & 7); col = o.mn0 + 8 * ((id >> 3) & 15); row_lim = o.k_lim; col_lim = o.mn_lim; }
-  else          { row = o.mn0 + (id & 127);              col = o.k0 + 8 * (id >> 7);         row_lim = o.mn_lim; col_lim = o.k_lim; }
+  else          { row = o.mn0 + 8 * (id >> 5) + (id & 7); col = o.k0 + 8 * ((id >> 3) & 3);  row_lim = o.mn_lim; col_lim = o.k_lim; }
   if (row >= row_lim || col >= col_lim) return;
   const float* p = o.ptr + (long long)row * o.ld + col;
   if (o.vec && col + 7 < col_lim) {
@@ -150,20 +153,24 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS, 2) gemm_tc_kernel(GemmParams 
   } else {
     // ================= MMA issuer =================
     const uint32_t idesc = tc::make_idesc_bf16_f32(TBM, n_eff) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16);
-    const uint64_t d0 = tc::make_smem_desc(tc::smem_u32(smem), 2048, 128);  // LBO = k-group stride, SBO = 8-row-group stride
+    // per-operand descriptors (LBO = k-group stride, SBO = 8-row-group stride; see the layout note above)
+    const uint64_t da0 = A_MN ? tc::make_smem_desc(tc::smem_u32(smem), 2048, 128) : tc::make_smem_desc(tc::smem_u32(smem), 128, 512);
+    const uint64_t db0 = B_MN ? tc::make_smem_desc(tc::smem_u32(smem), 2048, 128) : tc::make_smem_desc(tc::smem_u32(smem), 128, 512);
+    constexpr int A_KS = A_MN ? 4096 : 256, B_KS = B_MN ? 4096 : 256;   // byte advance per K=16 step
     for (int i = 0; i < n_tiles; ++i) {
       const int s = i % TSTAGES;
       mbar_wait_spin(&full[s], (i / TSTAGES) & 1);
       __syncwarp();
       tc::fence_after_thread_sync();
       if (tc::elect_one()) {
-        const uint64_t ds = d0 + (uint64_t)((s * STAGE_BYTES) >> 4);
+        const uint64_t dsa = da0 + (uint64_t)((s * STAGE_BYTES) >> 4);
+        const uint64_t dsb = db0 + (uint64_t)((s * STAGE_BYTES + 2 * PLANE_BYTES) >> 4);
 #pragma unroll
         for (int ks = 0; ks < TBK / 16; ++ks) {
-          const uint64_t a_hi = ds + (uint64_t)((ks * 4096) >> 4);
+          const uint64_t a_hi = dsa + (uint64_t)((ks * A_KS) >> 4);
           const uint64_t a_lo = a_hi + (uint64_t)(PLANE_BYTES >> 4);
-          const uint64_t b_hi = a_hi + (uint64_t)((2 * PLANE_BYTES) >> 4);
-          const uint64_t b_lo = a_hi + (uint64_t)((3 * PLANE_BYTES) >> 4);
+          const uint64_t b_hi = dsb + (uint64_t)((ks * B_KS) >> 4);
+          const uint64_t b_lo = b_hi + (uint64_t)(PLANE_BYTES >> 4);
           tc::mma_bf16_ss(tmem_base, a_lo, b_hi, idesc, (i | ks) != 0);
           tc::mma_bf16_ss(tmem_base, a_hi, b_lo, idesc, true);
           tc::mma_bf16_ss(tmem_base, a_hi, b_hi, idesc, true);
