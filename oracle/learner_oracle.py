@@ -160,7 +160,9 @@ class OracleLearner:
         self.actor_adam, self.critic_adam = {}, {}
         self.step_count = 0
 
-    def iteration(self, batch, keep=True):
+    def iteration(self, batch, keep=True, grad_hook=None):
+        """grad_hook(net_name, grads_dict) may replace gradients in place before the optimiser step (used to
+        model the data-parallel all-reduce: mean of per-rank gradients == gradient of the global batch)."""
         dt = self.dtype
         Bn, L, n = self.burn_in, self.learning, self.n_step
         obs, act = np.asarray(batch["obs"], dt), np.asarray(batch["act"], dt)
@@ -184,6 +186,8 @@ class OracleLearner:
             q, q_next, rew, term, burn_in=Bn, learning=L, n_step=n, gamma=self.gamma)
         d_out = np.concatenate((np.zeros((Bn,) + dq.shape[1:], dt), dq), 0)
         critic_grad, _, _ = net_backward(self.critic, c1, d_out, critic=True)
+        if grad_hook is not None:
+            grad_hook("critic", critic_grad)
         adam_step(self.critic, critic_grad, self.critic_adam, self.critic_lr)
         # --- actor update (learner.py:117-128)
         zeros = np.zeros((B, self.actor["l2.weight_hh"].shape[1]), dt)
@@ -198,6 +202,8 @@ class OracleLearner:
         d_out_a = np.zeros_like(a1["out"])
         d_out_a[1::2] = d_mu
         actor_grad, _, _ = net_backward(self.actor, a1, d_out_a, critic=False)
+        if grad_hook is not None:
+            grad_hook("actor", actor_grad)
         adam_step(self.actor, actor_grad, self.actor_adam, self.actor_lr)
         if self.step_count % self.target_interval == 0:
             self.target_actor = {k: v.copy() for k, v in self.actor.items()}
