@@ -4,20 +4,27 @@
 // lo*hi + hi*lo + hi*hi) into a TMEM accumulator; warps 0-3 read it back with tcgen05.ld for the fused
 // epilogue (bias / tanh / dtanh / add, or split-K reduction with vector red.global.add).
 //
-//   warps 0..7  producers: global fp32 -> registers (prefetched one tile ahead) -> split -> 16-byte st.shared
-//   warp  8     MMA issuer: waits `full[stage]`, 6 UTCHMMA per 32-deep stage, tcgen05.commit -> `empty[stage]`
-//   3-stage ring of 32 KB (A hi/lo + B hi/lo), 2 CTAs per SM (96 KB smem, 128 TMEM columns each).
+//   warps 0..7  producers: cp.async global fp32 -> raw smem ring (2 x 32 KB in flight per CTA: global/L2 latency is
+//               hidden here; a register-staged prefetch exposed one full load latency per k-tile, 57% of samples)
+//               -> ld.shared own slots -> split -> 16-byte st.shared into the UMMA operand stage
+//   warp  8     MMA issuer: waits `full`, 6 UTCHMMA per 32-deep stage, tcgen05.commit -> `empty`
+//   96 KB of shared memory and 128 TMEM columns per CTA: two CTAs per SM overlap each other's phases.
 #include "gemm.cuh"
 #include "tc05.cuh"
 
 namespace r2d2 {
 namespace {
 
-constexpr int TBM = 128, TBN = 128, TBK = 32, TSTAGES = 3;
+constexpr int TBM = 128, TBN = 128, TBK = 32;
+constexpr int TSTAGES = 1;                          // UMMA operand stages (bf16 hi/lo core matrices)
+constexpr int RSTAGES = 2;                          // raw fp32 stages filled by cp.async (global latency hidden here)
 constexpr int PRODUCER_WARPS = 8, TC_GEMM_THREADS = (PRODUCER_WARPS + 1) * 32;
 constexpr int PLANE_BYTES = 128 * TBK * 2;          // one bf16 plane of a 128 x 32 operand tile = 8 KB
 constexpr int STAGE_BYTES = 4 * PLANE_BYTES;        // A hi, A lo, B hi, B lo
-constexpr int TC_GEMM_SMEM = TSTAGES * STAGE_BYTES + 128;
+constexpr int RAW_STAGE_BYTES = 2 * 128 * TBK * 4;  // A + B tiles in fp32 = 32 KB
+constexpr int OFF_RAW = TSTAGES * STAGE_BYTES;
+constexpr int OFF_BARS = OFF_RAW + RSTAGES * RAW_STAGE_BYTES;
+constexpr int TC_GEMM_SMEM = OFF_BARS + 128;        // 96 KB + barriers: two CTAs per SM
 constexpr int GROUPS = 128 * TBK / 8;               // 512 groups of 8 elements per operand tile
 
 // one group = 8 consecutive elements along the operand's contiguous global dimension -> one 16-byte smem row
@@ -58,6 +65,39 @@ __device__ __forceinline__ void load_group(const OperandSrc& o, int id, float4& 
   }
 }
 
+// global coordinates of group `id` of a tile: pointer to its first element (or nullptr when the whole group is
+// out of range) and the number of valid elements (0..8)
+template <bool MN_MAJOR>
+__device__ __forceinline__ const float* group_src(const OperandSrc& o, int id, int& n_valid) {
+  int row, col, row_lim, col_lim;
+  if (MN_MAJOR) { row = o.k0 + 8 * (id >> 7) + (id & 7); col = o.mn0 + 8 * ((id >> 3) & 15); row_lim = o.k_lim; col_lim = o.mn_lim; }
+  else          { row = o.mn0 + 8 * (id >> 5) + (id & 7); col = o.k0 + 8 * ((id >> 3) & 3);  row_lim = o.mn_lim; col_lim = o.k_lim; }
+  if (row >= row_lim || col >= col_lim) { n_valid = 0; return nullptr; }
+  n_valid = min(8, col_lim - col);
+  return o.ptr + (long long)row * o.ld + col;
+}
+
+// 32 bytes of fp32 -> this thread's raw slot: two 16-byte cp.async with zero fill past `n_valid` elements; operands
+// whose rows are not 16-byte aligned (ld % 4 != 0: obs = 17 columns ...) go through registers instead
+template <bool MN_MAJOR>
+__device__ __forceinline__ void fetch_group(const OperandSrc& o, int id, unsigned char* raw_slot) {
+  int nv;
+  const float* src = group_src<MN_MAJOR>(o, id, nv);
+  if (o.vec) {
+    const uint32_t dst = tc::smem_u32(raw_slot);
+    const float* s0 = src ? src : o.ptr;
+    const int b0 = min(nv, 4) * 4, b1 = max(nv - 4, 0) * 4;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(s0), "r"(b0) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16), "l"(b1 ? s0 + 4 : o.ptr), "r"(b1) : "memory");
+  } else {
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = (i < nv) ? __ldg(src + i) : 0.f;
+    *reinterpret_cast<float4*>(raw_slot) = make_float4(t[0], t[1], t[2], t[3]);
+    *reinterpret_cast<float4*>(raw_slot + 16) = make_float4(t[4], t[5], t[6], t[7]);
+  }
+}
+
 __device__ __forceinline__ void store_group(unsigned char* hi_plane, unsigned char* lo_plane, int id, const float4& v0,
                                             const float4& v1) {
   uint4 h, l;
@@ -81,7 +121,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS, 2) gemm_tc_kernel(GemmParams 
   constexpr bool A_MN = (LAYOUT == GEMM_TN);   // A given as [K][M]
   constexpr bool B_MN = (LAYOUT != GEMM_NT);   // B given as [K][N]
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TSTAGES * STAGE_BYTES);  // [TSTAGES]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BARS);               // [TSTAGES]
   uint64_t* empty = full + TSTAGES;                                            // [TSTAGES]
   uint64_t* accum_full = empty + TSTAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
@@ -122,24 +162,36 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS, 2) gemm_tc_kernel(GemmParams 
         b = OperandSrc{p.B2, p.ldb2, n0, p.N, (t - nk1) * TBK, p.K2, vecB2};
       }
     };
-    float4 ra[2][2], rb[2][2];
-    auto load_tile = [&](int t) {
+    // raw slot of (stage r, operand op, group id): each thread only ever touches its own four slots, so the raw ring
+    // needs no block-level synchronisation - cp.async.wait_group is enough
+    auto raw_slot = [&](int r, int op, int id) { return smem + OFF_RAW + r * RAW_STAGE_BYTES + op * (RAW_STAGE_BYTES / 2) + id * 32; };
+    auto fetch_tile = [&](int t, int r) {
       OperandSrc a, b;
       src_of(t, a, b);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        load_group<A_MN>(a, tid + g * 256, ra[g][0], ra[g][1]);
-        load_group<B_MN>(b, tid + g * 256, rb[g][0], rb[g][1]);
+        fetch_group<A_MN>(a, tid + g * 256, raw_slot(r, 0, tid + g * 256));
+        fetch_group<B_MN>(b, tid + g * 256, raw_slot(r, 1, tid + g * 256));
       }
     };
-    load_tile(t_begin);
+    fetch_tile(t_begin, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (n_tiles > 1) fetch_tile(t_begin + 1, 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     for (int i = 0; i < n_tiles; ++i) {
-      const int s = i % TSTAGES;
+      const int s = i % TSTAGES, r = i % RSTAGES;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // tile i has landed (tile i+1 may still be in flight)
       float4 ca[2][2], cb[2][2];
 #pragma unroll
-      for (int g = 0; g < 2; ++g) { ca[g][0] = ra[g][0]; ca[g][1] = ra[g][1]; cb[g][0] = rb[g][0]; cb[g][1] = rb[g][1]; }
-      if (i + 1 < n_tiles) load_tile(t_begin + i + 1);       // prefetch the next tile's fp32 operands
-      mbar_wait_spin(&empty[s], ((i / TSTAGES) & 1) ^ 1);    // the MMAs that read this stage have retired
+      for (int g = 0; g < 2; ++g) {
+        const unsigned char* sa = raw_slot(r, 0, tid + g * 256);
+        const unsigned char* sb = raw_slot(r, 1, tid + g * 256);
+        ca[g][0] = *reinterpret_cast<const float4*>(sa); ca[g][1] = *reinterpret_cast<const float4*>(sa + 16);
+        cb[g][0] = *reinterpret_cast<const float4*>(sb); cb[g][1] = *reinterpret_cast<const float4*>(sb + 16);
+      }
+      if (i + RSTAGES < n_tiles) fetch_tile(t_begin + i + RSTAGES, r);   // the slot is free again: refill it
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      mbar_wait_spin(&empty[s], ((i / TSTAGES) & 1) ^ 1);    // the MMAs that read this operand stage have retired
       unsigned char* st = smem + s * STAGE_BYTES;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -150,6 +202,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS, 2) gemm_tc_kernel(GemmParams 
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
     // ================= MMA issuer =================
     const uint32_t idesc = tc::make_idesc_bf16_f32(TBM, n_eff) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16);
@@ -182,16 +235,25 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS, 2) gemm_tc_kernel(GemmParams 
     }
   }
 
-  // ================= epilogue: warps 0..3 own TMEM lane quarters 0..3 =================
-  if (w_u < 4) {
+  // ================= epilogue: all 8 producer warps; warp w owns TMEM lane quarter w%4 and column half w/4 ========
+  if (w_u < PRODUCER_WARPS) {
+    // bias tile -> shared (reuses the raw ring, which is idle now), so the per-column adds do not wait on global loads
+    float* s_bias = reinterpret_cast<float*>(smem + OFF_RAW);
+    if (p.bias) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");                  // every producer is done with the raw ring
+      if (tid < TBN) s_bias[tid] = (n0 + tid < p.N) ? __ldg(p.bias + n0 + tid) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     mbar_wait_spin(accum_full, 0);
     __syncwarp();
     tc::fence_after_thread_sync();
-    const int row = m0 + w_u * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(w_u * 32) << 16);
+    const int q = w_u & 3, half = w_u >> 2;
+    const int row = m0 + q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool vec_c = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
     const bool vec_z = p.Z && ((reinterpret_cast<uintptr_t>(p.Z) & 15) == 0) && (p.ldz % 4 == 0);
-    for (int c0 = 0; c0 < n_eff; c0 += 8) {
+    const int c_begin = half * (TBN / 2), c_end = min(n_eff, c_begin + TBN / 2);
+    for (int c0 = c_begin; c0 < c_end; c0 += 8) {
       float v[8];
       __syncwarp();                                          // tcgen05.ld is warp-collective: reconverge first
       tc::tmem_ld_32x32b_x8(lane_base + (uint32_t)c0, v);
@@ -200,7 +262,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS, 2) gemm_tc_kernel(GemmParams 
       const int nv = min(8, p.N - col);
       if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (j < nv) v[j] += __ldg(p.bias + col + j);
+        for (int j = 0; j < 8; ++j) v[j] += s_bias[c0 + j];
       }
       if (p.epilogue == EPI_TANH) {
 #pragma unroll
