@@ -46,10 +46,17 @@ long long launch_count();
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
-// ---- bf16 hi/lo split: x ~= hi + lo with 16 significant bits; products hi*hi + hi*lo + lo*hi ----
+// ---- bf16 hi/lo split: x ~= hi + lo with ~16 significant bits; products hi*hi + hi*lo + lo*hi.
+// Done with integer ops on the fp32 bit pattern (round-half-up on the magnitude, then keep the upper 16 bits): the
+// F2F.BF16.F32 conversion instruction runs on a 16/clk/SM pipe and made the operand staging of the tcgen05 GEMM
+// conversion-bound (2 conversions per element); IADD/LOP/PRMT/FADD issue at full rate.
+__device__ __forceinline__ uint32_t bf16_hi_bits(float x) { return (__float_as_uint(x) + 0x8000u) & 0xFFFF0000u; }
+
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  const uint32_t h = bf16_hi_bits(x);
+  const uint32_t l = bf16_hi_bits(x - __uint_as_float(h));
+  hi = __ushort_as_bfloat16((unsigned short)(h >> 16));
+  lo = __ushort_as_bfloat16((unsigned short)(l >> 16));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -57,12 +64,13 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// two consecutive elements -> one packed word per plane (x0 in the low half)
 __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 h0, l0, h1, l1;
-  split_bf16(x0, h0, l0);
-  split_bf16(x1, h1, l1);
-  hi = pack_bf16(h0, h1);
-  lo = pack_bf16(l0, l1);
+  const uint32_t h0 = bf16_hi_bits(x0), h1 = bf16_hi_bits(x1);
+  hi = __byte_perm(h0, h1, 0x7632);
+  const uint32_t l0 = __float_as_uint(x0 - __uint_as_float(h0)) + 0x8000u;
+  const uint32_t l1 = __float_as_uint(x1 - __uint_as_float(h1)) + 0x8000u;
+  lo = __byte_perm(l0, l1, 0x7632);
 }
 
 // mma.sync m16n8k16 bf16 x bf16 -> f32 (legacy tensor path; SASS: HMMA.16816.F32.BF16)
