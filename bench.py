@@ -60,27 +60,37 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self, begin):
+        """wall-clock window of the timed region: only samples taken inside it are reported"""
+        if begin:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def stop(self):
         if self.proc is not None:
+            time.sleep(0.06)
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.05]
+        rows = inside if inside else [r for _, r in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -181,8 +191,8 @@ def run_reference(args, c):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--episodes", type=int, default=384, help="episodes in the per-GPU replay shard")
@@ -229,19 +239,21 @@ def main():
         torch.cuda.synchronize()
 
     log("warm-up (HBM-resident arm)")
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()          # started before the warm-up so that samples exist when the timed region begins
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark(True)
     ev0.record()
     for _ in range(args.steps):
         step_resident()
     ev1.record()
     barrier()
+    clocks.mark(False)
     ms = ev0.elapsed_time(ev1) / args.steps
     clk = clocks.stop() if rank == 0 else None
     t_ms = torch.tensor([ms], device=dev)
@@ -323,7 +335,7 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "lstm_scan_fwd_kernel (persistent cluster LSTM scan, %d steps)" % S, "bound": "tensor",
+    roofline = {"kernel": "lstm_scan_fwd_tc_kernel (persistent cluster LSTM scan, tcgen05, W_hh in TMEM, %d cell steps)" % S, "bound": "tensor",
                 "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
                 "traffic": traffic, "peak_source": peaks["source"] + " bf16 dense burst (kernel timed alone)",
                 "us_per_step": scan_ms * 1e3 / S,
