@@ -218,6 +218,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: keep NCCL's banner / debug output out of it
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_bench_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     log(f"world={world} rank={rank}: building engine + replay shard")
     cfg = engine.PathConfig(**c)
