@@ -97,7 +97,8 @@ int r2d2_debug_scan_forward_trace(const float* gin, const float* whh, float* gat
                                   int H, long long* trace, r2d2_stream_t stream);
 /* debug: clusters of the tcgen05 scan kernel the device can keep resident at once (-1 if not instantiated) */
 int r2d2_debug_max_active_clusters(int H, int nb, int backward);
-/* GEMM implementation switch for A/B checks: 1 = tcgen05/TMEM (default), 0 = mma.sync v1 kernel */
+/* GEMM implementation switch for A/B checks: 1 = tcgen05/TMEM with skinny problems (K<64, N<32 or M<32) on the
+ * single-launch mma.sync kernel (default), 2 = tcgen05 for every shape, 0 = mma.sync v1 kernel only */
 int r2d2_set_gemm_impl(int impl);
 int r2d2_get_gemm_impl(void);
 /* scan implementation switch for A/B checks: 1 = tcgen05/TMEM (default), 0 = mma.sync v1 kernels */

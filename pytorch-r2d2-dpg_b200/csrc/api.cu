@@ -121,7 +121,11 @@ int r2d2_debug_scan_forward_trace(const float* gin, const float* whh, float* gat
 
 int r2d2_debug_max_active_clusters(int H, int nb, int backward) { return lstm_scan_max_active_clusters(H, nb, backward); }
 
-int r2d2_set_gemm_impl(int impl) { gemm_set_impl(impl); return R2D2_OK; }
+int r2d2_set_gemm_impl(int impl) {
+  gemm_set_impl(impl != 0);
+  gemm_set_impl_skinny_mma(impl != 2);  // 2 = force the tcgen05 path even for skinny problems (tests)
+  return R2D2_OK;
+}
 int r2d2_get_gemm_impl(void) { return gemm_get_impl(); }
 int r2d2_set_scan_impl(int impl) { lstm_scan_set_impl(impl); return R2D2_OK; }
 int r2d2_get_scan_impl(void) { return lstm_scan_get_impl(); }

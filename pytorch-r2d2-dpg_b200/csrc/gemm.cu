@@ -253,8 +253,13 @@ int gemm_get_impl() {
   return g_gemm_impl;
 }
 
+static int g_skinny_mma = 1;
+void gemm_set_impl_skinny_mma(int on) { g_skinny_mma = on ? 1 : 0; }
+int gemm_get_impl_skinny_mma() { return g_skinny_mma; }
+
 int gemm_suggest_split_k(int M, int N, int K) {
-  if (gemm_get_impl() == 1) return gemm_tc_suggest_split_k(M, N, K);
+  const bool skinny = (K < 64) || (N < 32) || (M < 32);
+  if (gemm_get_impl() == 1 && !(skinny && g_skinny_mma)) return gemm_tc_suggest_split_k(M, N, K);
   long long tiles = (long long)ceil_div(M, BM) * ceil_div(N, BN);
   int k_tiles = ceil_div(K, BK);
   if (tiles >= 148 || k_tiles < 16) return 1;
@@ -275,7 +280,15 @@ int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   R2D2_REQUIRE(p.K2 == 0 || (p.A2 && p.B2), "segment 2 operands");
   R2D2_REQUIRE((p.epilogue != EPI_MUL_DTANH && p.epilogue != EPI_ADD_Z) || p.Z, "epilogue needs Z");
   R2D2_REQUIRE(ceil_div(p.M, BM) <= 65535, "M too large for grid.y");
-  if (gemm_get_impl() == 1) return gemm_f32_tc(p, layout, stream);
+  // skinny problems (K < 64: obs/act inputs; N < 32: heads, dW1/dW3 blocks) are launch/latency bound: the single-launch
+  // mma.sync kernel beats pack + pack + tcgen05 there (tools/gemm_bench.py); everything else goes to the tcgen05 path
+  const bool skinny = (p.K + p.K2 < 64) || (p.N < 32) || (p.M < 32);
+  if (gemm_get_impl() == 1 && !(skinny && gemm_get_impl_skinny_mma())) {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("R2D2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (dbg) { GemmParams q = p; q.debug_flags = dbg; return gemm_f32_tc(q, layout, stream); }
+    return gemm_f32_tc(p, layout, stream);
+  }
   switch (layout) {
     case GEMM_NT: return launch_gemm<GEMM_NT>(p, stream);
     case GEMM_NN: return launch_gemm<GEMM_NN>(p, stream);

@@ -32,6 +32,7 @@ struct GemmParams {
   const float* Z = nullptr;  long long ldz = 0;   // [M,N] aux for the epilogue
   int epilogue = EPI_NONE;
   int split_k = 1;           // >1: partial products are atomically added into C (C must be pre-zeroed)
+  int debug_flags = 0;       // dev only (env R2D2_GEMM_DEBUG): 1 = producers skip fetch+convert, 2 = skip MMAs, 4 = skip epilogue stores
 };
 
 int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream);
@@ -41,6 +42,9 @@ int gemm_suggest_split_k(int M, int N, int K);
 // implementation: 1 = tcgen05/TMEM kernel (default), 0 = mma.sync v1 kernel; env R2D2_GEMM_IMPL = "tc" | "mma"
 void gemm_set_impl(int impl);
 int gemm_get_impl();
+// with the tcgen05 implementation selected, skinny problems still take the single-launch mma.sync kernel (default on)
+void gemm_set_impl_skinny_mma(int on);
+int gemm_get_impl_skinny_mma();
 int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream);
 int gemm_tc_suggest_split_k(int M, int N, int K);
 

@@ -166,5 +166,12 @@ __device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster_addr, 
                : "memory");
 }
 
+// bulk copy global -> own shared memory, completing `bytes` on an mbarrier of this CTA (1-D TMA, no tensor map)
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem_addr, const void* src_global, uint32_t bytes, uint32_t mbar_smem_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem_addr),
+               "l"(src_global), "r"(bytes), "r"(mbar_smem_addr)
+               : "memory");
+}
+
 }  // namespace tc
 }  // namespace r2d2

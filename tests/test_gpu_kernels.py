@@ -52,7 +52,7 @@ GEMM_CASES = [
 
 @pytest.fixture(params=["tc", "mma"])
 def gemm_impl(request, nv):
-    nv.lib().r2d2_set_gemm_impl(1 if request.param == "tc" else 0)
+    nv.lib().r2d2_set_gemm_impl(2 if request.param == "tc" else 0)   # 2: tcgen05 path for every shape, incl. skinny
     yield request.param
     nv.lib().r2d2_set_gemm_impl(1)
 
