@@ -26,7 +26,7 @@ int* scan_error_flag();  // device int, 0 = ok (defined below)
 
 namespace {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 512, TC_WARPS = 16;
 constexpr int GT_LD = 128 + 4;
 
 // Cell non-linearities on the serial chain: exp via MUFU.EX2 (__expf, ~2 ulp) and an approximate reciprocal
@@ -54,18 +54,21 @@ __device__ __forceinline__ void split8_store(const float4 v0, const float4 v1, u
 
 template <int H, int NB>
 struct TcFwdSmem {
-  static constexpr int C = H / 32, KC = H / 8;
-  static constexpr int HB_PLANE = KC * NB * 16;   // bytes of one plane of the h operand (all H units, NB rows)
-  static constexpr int OFF_HB = 0;                               // [buf][rank slice][plane][4 chunks][NB][8 bf16]
-  // tensor memory columns: NACC independent accumulators D_a at [a*NB, ..) (a chain of dependent N=16 MMAs into ONE
-  // accumulator runs at the MMA pipeline latency, ~25 ns each, not at its throughput), then the W_hh slice: hi plane
-  // at 128 (H/2 columns: two bf16 per column), lo plane after it
+  static constexpr int C = H / 32, KC = H / 8, RG = NB / 8;
+  // h operand tile, ROW-GROUP major so that (a) only row groups that hold real batch rows travel through DSMEM and
+  // (b) a row group can leave as soon as its cells are done:  [buf][row group g][slice r = source CTA][plane hi/lo]
+  // [4 k-chunks][8 rows][16 B]  ->  MMA descriptor LBO (k-chunk stride) = 128, SBO (row-group stride) = C*1024
+  static constexpr int SLICE = 1024;                 // one CTA's 32 units x 8 rows x (hi+lo)
+  static constexpr int RG_BYTES = C * SLICE;
+  static constexpr int BUF_BYTES = RG * RG_BYTES;    // = NB * H * 4
+  static constexpr int OFF_HB = 0;
+  // tensor memory columns: NACC independent accumulators D_a at [a*NB, ..), then the W_hh slice: hi plane at 128
+  // (H/2 columns: two bf16 per column), lo plane after it
   static constexpr int NACC = (H / 16) < 4 ? (H / 16) : 4;
   static constexpr int TM_A_HI = 128, TM_A_LO = 128 + H / 2, TM_COLS = 512;
-  static constexpr int OFF_GT = OFF_HB + 4 * HB_PLANE;           // fp32 [NB][GT_LD]
-  static constexpr int OFF_HSTAGE = OFF_GT + NB * GT_LD * 4;     // [dbuf][plane][4 chunks][NB][8] bf16
-  static constexpr int HSTAGE_PLANE = 4 * NB * 16;               // bytes of one CTA's slice of one plane
-  static constexpr int OFF_BAR = OFF_HSTAGE + 4 * HSTAGE_PLANE;  // 3 mbarriers + tmem slot + dead flag
+  static constexpr int OFF_GT = OFF_HB + 2 * BUF_BYTES;            // fp32 [NB][GT_LD]
+  static constexpr int OFF_HSTAGE = OFF_GT + NB * GT_LD * 4;       // [dbuf][row group][plane][4 chunks][8][16 B]
+  static constexpr int OFF_BAR = OFF_HSTAGE + 2 * RG * SLICE;      // 3 mbarriers + tmem slot + dead flag
   static constexpr int BYTES = OFF_BAR + 64;
   static_assert(BYTES <= 232448, "forward scan tile does not fit in 227 KB of shared memory");
 };
@@ -73,13 +76,15 @@ struct TcFwdSmem {
 template <int H, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwdParams p, int* err) {
   using SM = TcFwdSmem<H, NB>;
-  constexpr int C = SM::C, KC = SM::KC, KS = H / 16, NT = NB / 8;
+  constexpr int C = SM::C, KC = SM::KC, KS = H / 16, RG = SM::RG, NT = RG / 2;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b0 = (blockIdx.x / C) * p.rows_per_cluster;  // this cluster's batch rows [b0, b_end), at most NB of them
   const int b_end = min(p.B, b0 + p.rows_per_cluster);
+  const int n_rg_valid = (b_end - b0 + 7) >> 3;          // row groups that carry real rows
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform warp index (role dispatch)
+  const int r8 = w & 7, half = w >> 3;                   // pointwise role: row r8 of row groups e = half, half+2, ...
   const int B = p.B, S = p.T * p.repeat;
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
     *dead = 0;
   }
   if (w == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, SM::TM_COLS); }
-  // ---- initial h tile (all H units of my NB rows) -> operand buffer 0
+  // ---- initial h tile (all H units of my rows) -> operand buffer 0 (zeros for rows past b_end)
   for (int idx = tid; idx < NB * KC; idx += TC_THREADS) {
     const int n = idx % NB, kc = idx / NB, b = b0 + n;
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
@@ -108,21 +113,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
       v0 = __ldg(reinterpret_cast<const float4*>(src));
       v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
     }
-    unsigned char* dst = hb + (kc >> 2) * 2 * SM::HSTAGE_PLANE + (kc & 3) * NB * 16 + n * 16;  // buffer 0
-    split8_store(v0, v1, dst, dst + SM::HSTAGE_PLANE);
+    unsigned char* dst = hb + (n >> 3) * SM::RG_BYTES + (kc >> 2) * SM::SLICE + (kc & 3) * 128 + (n & 7) * 16;
+    split8_store(v0, v1, dst, dst + 512);
   }
   const int ug = rank * 32 + lane;
   float cst[NT];
 #pragma unroll
-  for (int e = 0; e < NT; ++e) {
-    const int b = b0 + w + 8 * e;
-    cst[e] = 0.f;
+  for (int j = 0; j < NT; ++j) {
+    const int b = b0 + 8 * (half + 2 * j) + r8;
+    cst[j] = 0.f;
     if (b < b_end) {
       const float hv = p.h0 ? __ldg(p.h0 + (size_t)b * H + ug) : 0.f;
       const float cv = p.c0 ? __ldg(p.c0 + (size_t)b * H + ug) : 0.f;
       p.hs[(size_t)b * H + ug] = hv;
       p.cs[(size_t)b * H + ug] = cv;
-      cst[e] = cv;
+      cst[j] = cv;
     }
   }
   tc::fence_proxy_async_smem();
@@ -133,12 +138,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
   // ---- W_hh slice -> TENSOR MEMORY, resident for the whole launch: TMEM lane r = local gate row (gate = r/32 =
   // lane quarter, unit = r%32), columns = K packed two bf16 per 32-bit word (hi plane, then lo plane).
   {
-    const int q = w & 3, ch = w >> 2;
+    const int q = w & 3;
     const float* wrow = p.whh + (size_t)(q * H + rank * 32 + lane) * H;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     __syncwarp();
 #pragma unroll 1
-    for (int ks = ch * (KS / 2); ks < (ch + 1) * (KS / 2); ++ks) {
+    for (int ks = (w >> 2); ks < KS; ks += TC_WARPS / 4) {
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -159,9 +164,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
   const uint32_t idesc = tc::make_idesc_bf16_f32(128, NB);
   const uint32_t hb_addr = tc::smem_u32(hb);
   // the operand descriptor is loop invariant up to its 16-byte start-address field: build once, add offsets per k-step
-  const uint64_t db_hi0 = tc::make_smem_desc(hb_addr, NB * 16, 128);   // buffer 0, slice 0, plane hi
+  const uint64_t db_hi0 = tc::make_smem_desc(hb_addr, 128, SM::RG_BYTES);   // buffer 0, slice 0, plane hi
   const size_t gstride = (size_t)4 * H;
-  constexpr uint32_t STEP_TX = (uint32_t)C * 2u * (uint32_t)SM::HSTAGE_PLANE;
+  const uint32_t step_tx = (uint32_t)(C * n_rg_valid * SM::SLICE);
 
   for (int s = 0; s < S; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
@@ -169,29 +174,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
 
     float gpre[NT][4];
 #pragma unroll
-    for (int e = 0; e < NT; ++e) {
-      const int b = b0 + w + 8 * e;
+    for (int j = 0; j < NT; ++j) {
+      const int b = b0 + 8 * (half + 2 * j) + r8;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        gpre[e][q] = (b < b_end) ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;  // plain load: gates may alias gin
+        gpre[j][q] = (b < b_end) ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;  // plain load: gates may alias gin
     }
 
     TRACE_STAMP(0);
     if (w_u == 0) {  // MMA warp (warp-uniform branch); one elected lane issues
-      if (s + 1 < S && tc::elect_one()) tc::mbar_arrive_expect_tx(&h_full[nxt], STEP_TX);  // h_s of all C CTAs -> buffer nxt
+      if (s + 1 < S && tc::elect_one()) tc::mbar_arrive_expect_tx(&h_full[nxt], step_tx);  // h_s of all C CTAs -> buffer nxt
       if (s > 0 && !*dead) {
         if (!tc::mbar_wait(&h_full[cur], ((s - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 1); }
       }
       __syncwarp();
       TRACE_STAMP(1);
       tc::fence_after_thread_sync();
-      const uint64_t db_cur = db_hi0 + (uint64_t)((cur * 2 * SM::HB_PLANE) >> 4);
+      const uint64_t db_cur = db_hi0 + (uint64_t)((cur * SM::BUF_BYTES) >> 4);
       if (tc::elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const uint32_t ta_hi = tmem_base + SM::TM_A_HI + ks * 8, ta_lo = tmem_base + SM::TM_A_LO + ks * 8;
-        const uint64_t db_hi = db_cur + (uint64_t)(((ks >> 1) * 2 * SM::HSTAGE_PLANE + (ks & 1) * 2 * NB * 16) >> 4);
-        const uint64_t db_lo = db_hi + (uint64_t)(SM::HSTAGE_PLANE >> 4);
+        const uint64_t db_hi = db_cur + (uint64_t)(((ks >> 1) * SM::SLICE + (ks & 1) * 256) >> 4);
+        const uint64_t db_lo = db_hi + (uint64_t)(512 >> 4);
         const uint32_t d = tmem_base + (ks % SM::NACC) * NB;
         tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks >= SM::NACC);
         tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
@@ -209,68 +214,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
     tc::fence_after_thread_sync();
     __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the spin wait
 
-    // ---- accumulator -> gate tile: warp w reads TMEM lanes 32*(w&3).. (gate w&3, unit = lane), column half w>>2
-    {
-      const int q = w & 3, ch = w >> 2;
+    // ---- accumulator -> gate tile: warp w reads TMEM lanes 32*(w&3).. (gate w&3, unit = lane), 8-column block w>>2
+    if ((w >> 2) * 8 < NB) {
+      const int q = w & 3, c0 = (w >> 2) * 8;
+      float v[8];
+      tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-      for (int part = 0; part < NB / 16; ++part) {
-        const int c0 = ch * (NB / 2) + part * 8;
-        float v[8];
-        tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      for (int a = 1; a < SM::NACC; ++a) {
+        float u[8];
+        tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NB + c0), u);
 #pragma unroll
-        for (int a = 1; a < SM::NACC; ++a) {
-          float u[8];
-          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NB + c0), u);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += u[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gt[(c0 + j) * GT_LD + q * 32 + lane] = v[j];
+        for (int j = 0; j < 8; ++j) v[j] += u[j];
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gt[(c0 + j) * GT_LD + q * 32 + lane] = v[j];
     }
     tc::fence_before_thread_sync();
     __syncthreads();
     TRACE_STAMP(4);
 
-    // ---- pointwise LSTM cell: thread = (unit = lane, batch column n = w + 8e); coalesced along units
-    unsigned char* hs_buf = hstage + (s & 1) * 2 * SM::HSTAGE_PLANE;
+    // ---- pointwise LSTM cell, one row group at a time: thread = (unit = lane, row r8 of group e); as soon as the 8
+    // warps of this half have finished a group, its 1 KB slice (hi+lo) leaves for every CTA of the cluster, overlapping
+    // the DSMEM transfer (~20 B/clk/SM) with the cells of the next group and with the other half's work
+    unsigned char* hs_buf = hstage + (s & 1) * RG * SM::SLICE;
 #pragma unroll
-    for (int e = 0; e < NT; ++e) {
-      const int n = w + 8 * e, b = b0 + n;
-      __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
-      if (b < b_end) {
-        const float* gr = gt + n * GT_LD + lane;
-        const float ig = fast_sigmoid(gr[0] + gpre[e][0]);
-        const float fg = fast_sigmoid(gr[32] + gpre[e][1]);
-        const float gg = fast_tanh(gr[64] + gpre[e][2]);
-        const float og = fast_sigmoid(gr[96] + gpre[e][3]);
-        const float cn = fg * cst[e] + ig * gg;
-        const float hn = og * fast_tanh(cn);
-        cst[e] = cn;
-        float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
-        go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
-        p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
-        p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
-        if (p.head_in && (s % p.repeat) == p.repeat - 1)
-          p.head_in[((size_t)t * B + b) * H + ug] = fast_tanh(hn);
-        split_bf16(hn, hi, lo);
+    for (int j = 0; j < NT; ++j) {
+      const int e = half + 2 * j;
+      if (e < n_rg_valid) {
+        const int n = 8 * e + r8, b = b0 + n;
+        __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+        if (b < b_end) {
+          const float* gr = gt + n * GT_LD + lane;
+          const float ig = fast_sigmoid(gr[0] + gpre[j][0]);
+          const float fg = fast_sigmoid(gr[32] + gpre[j][1]);
+          const float gg = fast_tanh(gr[64] + gpre[j][2]);
+          const float og = fast_sigmoid(gr[96] + gpre[j][3]);
+          const float cn = fg * cst[j] + ig * gg;
+          const float hn = og * fast_tanh(cn);
+          cst[j] = cn;
+          float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
+          go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
+          p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
+          p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
+          if (p.head_in && (s % p.repeat) == p.repeat - 1)
+            p.head_in[((size_t)t * B + b) * H + ug] = fast_tanh(hn);
+          split_bf16(hn, hi, lo);
+        }
+        unsigned char* dst = hs_buf + e * SM::SLICE + (lane >> 3) * 128 + r8 * 16 + (lane & 7) * 2;  // [plane][chunk][row][8]
+        *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(dst + 512) = lo;
+        tc::fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");   // the 8 warps that own this row group
+        if (s + 1 < S && r8 < C && tc::elect_one()) {
+          const uint32_t d = r8;
+          const uint32_t dst_local = hb_addr + nxt * SM::BUF_BYTES + e * SM::RG_BYTES + rank * SM::SLICE;
+          tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf + e * SM::SLICE), SM::SLICE,
+                                   tc::mapa(tc::smem_u32(&h_full[nxt]), d));
+        }
       }
-      const int off = ((lane >> 3) * NB + n) * 16 + (lane & 7) * 2;  // [chunk][n][8]
-      *reinterpret_cast<__nv_bfloat16*>(hs_buf + off) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(hs_buf + SM::HSTAGE_PLANE + off) = lo;
-    }
-    TRACE_STAMP(5);
-    tc::fence_proxy_async_smem();
-    __syncthreads();
-    TRACE_STAMP(6);
-
-    // ---- all-gather of h_s: one bulk copy (hi+lo planes, contiguous) per destination CTA, issued by lane 0 of
-    // warp d so the C copies leave from different schedulers; each completes on the destination's barrier
-    if (s + 1 < S && w_u < C && tc::elect_one()) {
-      const uint32_t d = w_u;
-      const uint32_t dst_local = hb_addr + nxt * 2 * SM::HB_PLANE + rank * 2 * SM::HSTAGE_PLANE;
-      tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf), 2 * SM::HSTAGE_PLANE,
-                               tc::mapa(tc::smem_u32(&h_full[nxt]), d));
     }
     TRACE_STAMP(7);
   }
@@ -304,13 +305,15 @@ struct TcBwdSmem {
 template <int H, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwdParams p, int* err) {
   using SM = TcBwdSmem<H, NB>;
-  constexpr int C = SM::C, MT = SM::MT, NT = NB / 8;
+  constexpr int C = SM::C, MT = SM::MT, RG = NB / 8, NT = RG / 2;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b0 = (blockIdx.x / C) * p.rows_per_cluster;  // this cluster's batch rows [b0, b_end), at most NB of them
   const int b_end = min(p.B, b0 + p.rows_per_cluster);
+  const int n_valid = b_end - b0;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int r8 = w & 7, half = w >> 3;                   // pointwise role: row r8 of row groups e = half, half+2, ...
   const int B = p.B, S = p.T * p.repeat;
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -334,11 +337,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   const size_t gstride = (size_t)4 * H;
   float dcn[NT], keep[NT][4];
 #pragma unroll
-  for (int e = 0; e < NT; ++e) {
-    dcn[e] = 0.f;
+  for (int j = 0; j < NT; ++j) {
+    dcn[j] = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) keep[e][q] = 0.f;
+    for (int q = 0; q < 4; ++q) keep[j][q] = 0.f;
   }
+  // rows of the operand tile that never carry a batch row stay zero for the whole launch
+  for (int idx = tid; idx < 2 * SM::DG_PLANE / 16; idx += TC_THREADS) reinterpret_cast<uint4*>(dgs)[idx] = make_uint4(0, 0, 0, 0);
   tc::fence_proxy_async_smem();
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -347,14 +352,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   // ---- A(j, r) = W_hh[grow(r)][j] -> TENSOR MEMORY: lane = output unit j within the 128-row tile mt, K index
   // r = local gate row (gate*32 + unit) packed two per column; rows j >= H are zero
   {
-    const int q = w & 3, ch = w >> 2;
+    const int q = w & 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     __syncwarp();
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int j = mt * 128 + q * 32 + lane;
 #pragma unroll 1
-      for (int ks = ch * 4; ks < ch * 4 + 4; ++ks) {
+      for (int ks = (w >> 2); ks < 8; ks += TC_WARPS / 4) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -377,7 +382,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
 
   const uint32_t idesc = tc::make_idesc_bf16_f32(128, NB);
   const uint64_t db_hi0 = tc::make_smem_desc(tc::smem_u32(dgs), NB * 16, 128);
-  constexpr uint32_t STEP_TX = (uint32_t)C * (uint32_t)SM::PS_SLOT;
+  const uint32_t slot_bytes = (uint32_t)n_valid * 128u;            // only rows that exist travel: [n][32 units] fp32
+  const uint32_t step_tx = (uint32_t)C * slot_bytes;
 
   for (int it = 0; it < S; ++it) {
     const int s = S - 1 - it;
@@ -389,63 +395,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     // prefetch the saved activations of this step before waiting for the partial sums
     float pg[NT][4], pc_prev[NT], pc_new[NT], phead[NT];
 #pragma unroll
-    for (int e = 0; e < NT; ++e) {
-      const int b = b0 + w + 8 * e;
-      pc_prev[e] = pc_new[e] = phead[e] = 0.f;
+    for (int j = 0; j < NT; ++j) {
+      const int b = b0 + 8 * (half + 2 * j) + r8;
+      pc_prev[j] = pc_new[j] = phead[j] = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) pg[e][q] = 0.f;
+      for (int q = 0; q < 4; ++q) pg[j][q] = 0.f;
       if (b < b_end) {
         const float* gs = p.gates + ((size_t)s * B + b) * gstride + ug;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) pg[e][q] = gs[q * H];
-        pc_prev[e] = __ldg(p.cs + ((size_t)s * B + b) * H + ug);
-        pc_new[e] = __ldg(p.cs + ((size_t)(s + 1) * B + b) * H + ug);
-        if (has_head) phead[e] = __ldg(p.dh_head + ((size_t)(rel / p.repeat) * B + b) * H + ug);
+        for (int q = 0; q < 4; ++q) pg[j][q] = gs[q * H];
+        pc_prev[j] = __ldg(p.cs + ((size_t)s * B + b) * H + ug);
+        pc_new[j] = __ldg(p.cs + ((size_t)(s + 1) * B + b) * H + ug);
+        if (has_head) phead[j] = __ldg(p.dh_head + ((size_t)(rel / p.repeat) * B + b) * H + ug);
       }
     }
     if (it > 0 && !*dead) {
       if (!tc::mbar_wait(&ps_full[buf], ((it - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 3); }
     }
 
-    // ---- pointwise backward of the cell (thread = (unit = lane, n = w + 8e))
+    // ---- pointwise backward of the cell (thread = (unit = lane, row r8 of row group e))
 #pragma unroll
-    for (int e = 0; e < NT; ++e) {
-      const int n = w + 8 * e, b = b0 + n;
-      float dg[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < NT; ++j) {
+      const int n = 8 * (half + 2 * j) + r8, b = b0 + n;
       if (b < b_end) {
-        float dh = phead[e];
+        float dg[4];
+        float dh = phead[j];
         if (it > 0) {
 #pragma unroll
           for (int src = 0; src < C; ++src) dh += ps[((buf * C + src) * NB + n) * 32 + lane];
         }
-        const float ig = pg[e][0], fg = pg[e][1], gg = pg[e][2], og = pg[e][3];
-        const float tcn = fast_tanh(pc_new[e]);
-        const float dc = dcn[e] + dh * og * (1.f - tcn * tcn);
+        const float ig = pg[j][0], fg = pg[j][1], gg = pg[j][2], og = pg[j][3];
+        const float tcn = fast_tanh(pc_new[j]);
+        const float dc = dcn[j] + dh * og * (1.f - tcn * tcn);
         dg[3] = dh * tcn * og * (1.f - og);
         dg[0] = dc * gg * ig * (1.f - ig);
-        dg[1] = dc * pc_prev[e] * fg * (1.f - fg);
+        dg[1] = dc * pc_prev[j] * fg * (1.f - fg);
         dg[2] = dc * ig * (1.f - gg * gg);
-        dcn[e] = dc * fg;
+        dcn[j] = dc * fg;
         float* go = p.dgates + ((size_t)s * B + b) * gstride + ug;
         go[0] = dg[0]; go[H] = dg[1]; go[2 * H] = dg[2]; go[3 * H] = dg[3];
         if (p.repeat > 1) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) keep[e][q] += dg[q];
+          for (int q = 0; q < 4; ++q) keep[j][q] += dg[q];
           if (s % p.repeat == 0) {
             float* gi = p.dgin + ((size_t)t * B + b) * gstride + ug;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { gi[q * H] = keep[e][q]; keep[e][q] = 0.f; }
+            for (int q = 0; q < 4; ++q) { gi[q * H] = keep[j][q]; keep[j][q] = 0.f; }
           }
         }
-      }
-      // operand tile of the MMA: K index r = q*32 + lane -> chunk (q*4 + lane/8), element lane%8
+        // operand tile of the MMA: K index r = q*32 + lane -> chunk (q*4 + lane/8), element lane%8
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(dg[q], hi, lo);
-        const int off = ((q * 4 + (lane >> 3)) * NB + n) * 16 + (lane & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(dgs + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(dgs + SM::DG_PLANE + off) = lo;
+        for (int q = 0; q < 4; ++q) {
+          __nv_bfloat16 hi, lo;
+          split_bf16(dg[q], hi, lo);
+          const int off = ((q * 4 + (lane >> 3)) * NB + n) * 16 + (lane & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(dgs + off) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(dgs + SM::DG_PLANE + off) = lo;
+        }
       }
     }
     if (s == 0) break;  // dh_{-1} is not needed: the initial state is data, not a parameter
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     if (w_u == 0) {
       tc::fence_after_thread_sync();
       if (tc::elect_one()) {
-      tc::mbar_arrive_expect_tx(&ps_full[buf ^ 1], STEP_TX);
+      tc::mbar_arrive_expect_tx(&ps_full[buf ^ 1], step_tx);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -484,26 +490,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     // ---- partial sums -> staging [owner CTA][n][32 units]; lane = output unit j within the 128-row tile
     float* pst = pstage + (size_t)(it & 1) * C * NB * 32;
     {
-      const int q = w & 3, ch = w >> 2;
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
+      const int q = w & 3;
+      for (int idx = (w >> 2); idx < MT * RG; idx += TC_WARPS / 4) {
+        const int mt = idx / RG, c0 = (idx % RG) * 8;
         const int j = mt * 128 + q * 32 + lane;
+        float v[8];
+        tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * SM::NACC * NB + c0), v);
 #pragma unroll
-        for (int part = 0; part < NB / 16; ++part) {
-          const int c0 = ch * (NB / 2) + part * 8;
-          float v[8];
-          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * SM::NACC * NB + c0), v);
+        for (int a = 1; a < SM::NACC; ++a) {
+          float u[8];
+          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * SM::NACC + a) * NB + c0), u);
 #pragma unroll
-          for (int a = 1; a < SM::NACC; ++a) {
-            float u[8];
-            tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * SM::NACC + a) * NB + c0), u);
+          for (int i = 0; i < 8; ++i) v[i] += u[i];
+        }
+        if (j < H) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += u[i];
-          }
-          if (j < H) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pst[(((j >> 5) * NB) + c0 + i) * 32 + (j & 31)] = v[i];
-          }
+          for (int i = 0; i < 8; ++i) pst[(((j >> 5) * NB) + c0 + i) * 32 + (j & 31)] = v[i];
         }
       }
     }
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       const uint32_t d = w_u;
       const uint32_t src = tc::smem_u32(pst + (size_t)d * NB * 32);
       const uint32_t dst_local = tc::smem_u32(ps + ((size_t)((buf ^ 1) * C + rank) * NB) * 32);
-      tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, SM::PS_SLOT, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
+      tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, slot_bytes, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
     }
   }
   tc::fence_before_thread_sync();

@@ -18,13 +18,13 @@ for _ in range(2):
                                                nv.dptr(trace, torch.int64), nv.current_stream()))
 torch.cuda.synchronize()
 t = trace.cpu().numpy().astype(np.float64)          # [grid][S][8] ns
-names = ["top", "h_arrived", "mma_issued", "mma_done", "tmem_ld+sync", "pointwise", "fence+sync", "copies_issued"]
+names = ["top", "h_arrived", "mma_issued", "mma_done", "tmem_ld+sync", "-", "-", "cells+copies_issued"]
 cl = t[:C]                                           # cluster 0
 steps = slice(8, S - 1)
 print(f"H={H} B={B} NB={NB} grid={grid}; mean ns per phase (cluster 0, rank 0), steps 8..{S-2}")
 r0 = cl[0]
-for i in range(1, 8):
-    print(f"  {names[i-1]:>14s} -> {names[i]:<14s} {np.mean(r0[steps, i] - r0[steps, i-1]):8.1f} ns")
+for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 7)):
+    print(f"  {names[a]:>14s} -> {names[b]:<20s} {np.mean(r0[steps, b] - r0[steps, a]):8.1f} ns")
 print(f"  step period {np.mean(np.diff(r0[steps, 0])):8.1f} ns")
 # copy latency: my h_arrived(s+1) minus the latest copies_issued(s) among the ranks of the cluster
 lat = cl[0][9:S-1, 1] - cl[:, 8:S-2, 7].max(axis=0)
