@@ -14,6 +14,7 @@
 //     (the v1 kernel spent 24% of its samples in the barrier's release fence, profiles/r01_*).
 // Backward: P[H x NB] = W_slice^T [H x 128] * dG^T via tcgen05, fp32 partial sums reduce-scattered with bulk copies.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "lstm_scan.cuh"
 #include "tc05.cuh"
@@ -281,6 +282,249 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, ping-pong variant for clusters that own 17..32 batch rows: the rows are split into two sub-tiles of
+// <= 16 rows (one N=16 MMA tile each) that alternate through the pipeline, so the DSMEM all-gather and the cell math
+// of one sub-tile overlap with the tensor-core step of the other.  A dedicated 17th warp issues the MMAs; the 16
+// cell warps never block on the exchange.  Iteration k handles sub-tile k % 2 of cell step k / 2.
+// ------------------------------------------------------------------------------------------------
+constexpr int PP_THREADS = 544, PP_CELL_WARPS = 16;
+
+template <int H>
+struct PpFwdSmem {
+  static constexpr int C = H / 32, KC = H / 8;
+  static constexpr int SLICE = 1024;                      // one CTA's 32 units x 8 rows x (hi+lo)
+  static constexpr int RG_BYTES = C * SLICE;
+  static constexpr int BUF_BYTES = 2 * RG_BYTES;          // 16 rows
+  static constexpr int OFF_HB = 0;                        // [sub][buf][row group][slice][plane][4 chunks][8][16 B]
+  static constexpr int NACC = (H / 16) < 4 ? (H / 16) : 4;
+  static constexpr int TM_A_HI = 128, TM_A_LO = 128 + H / 2, TM_COLS = 512;   // D[sub][acc] at (sub*4 + acc)*16
+  static constexpr int OFF_GT = OFF_HB + 4 * BUF_BYTES;   // fp32 [2 (iteration parity)][16][GT_LD]
+  static constexpr int OFF_HSTAGE = OFF_GT + 2 * 16 * GT_LD * 4;   // [sub][step parity][row group][SLICE]
+  static constexpr int OFF_BAR = OFF_HSTAGE + 8 * SLICE;  // h_full[sub][2], mma_done[sub], tmem slot, dead
+  static constexpr int BYTES = OFF_BAR + 96;
+  static_assert(BYTES <= 232448, "ping-pong scan tile does not fit in shared memory");
+};
+
+template <int H>
+__global__ void __launch_bounds__(PP_THREADS, 1) lstm_scan_fwd_pp_kernel(ScanFwdParams p, int* err) {
+  using SM = PpFwdSmem<H>;
+  constexpr int C = SM::C, KC = SM::KC, KS = H / 16;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / C) * p.rows_per_cluster;
+  const int b_end = min(p.B, b0 + p.rows_per_cluster);
+  const int n_rows = b_end - b0;                                   // 1..32
+  const int n_sub = n_rows > 16 ? 2 : 1;
+  const int rows0 = n_sub == 2 ? (n_rows + 1) / 2 : n_rows;         // rows of sub-tile 0; sub-tile 1 gets the rest
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int B = p.B, S = p.T * p.repeat;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* hb = smem + SM::OFF_HB;
+  float* gt_all = reinterpret_cast<float*>(smem + SM::OFF_GT);
+  unsigned char* hstage = smem + SM::OFF_HSTAGE;
+  uint64_t* h_full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);   // [sub][2]
+  uint64_t* mma_done = h_full + 4;                                      // [sub]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
+  volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&h_full[i], 1);
+    tc::mbar_init(&mma_done[0], 1);
+    tc::mbar_init(&mma_done[1], 1);
+    tc::fence_mbar_init_cluster();
+    *dead = 0;
+  }
+  if (w == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, SM::TM_COLS); }
+  auto sub_row0 = [&](int sub) { return sub == 0 ? 0 : rows0; };          // first cluster-local row of a sub-tile
+  auto sub_rows = [&](int sub) { return sub == 0 ? rows0 : n_rows - rows0; };
+  // ---- initial h tiles -> buffer 0 of each sub-tile (zeros for rows that do not exist)
+  for (int idx = tid; idx < 2 * 16 * KC; idx += PP_THREADS) {
+    const int sub = idx / (16 * KC), rem = idx % (16 * KC);
+    const int n = rem % 16, kc = rem / 16;
+    const int b = b0 + sub_row0(sub) + n;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (sub < n_sub && n < sub_rows(sub) && p.h0) {
+      const float* src = p.h0 + (size_t)b * H + kc * 8;
+      v0 = __ldg(reinterpret_cast<const float4*>(src));
+      v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+    }
+    unsigned char* dst = hb + (sub * 2 + 0) * SM::BUF_BYTES + (n >> 3) * SM::RG_BYTES + (kc >> 2) * SM::SLICE + (kc & 3) * 128 + (n & 7) * 16;
+    split8_store(v0, v1, dst, dst + 512);
+  }
+  const int ug = rank * 32 + lane;
+  float cst[2] = {0.f, 0.f};
+  if (w < PP_CELL_WARPS) {
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      if (sub < n_sub && w < sub_rows(sub)) {
+        const int b = b0 + sub_row0(sub) + w;
+        const float hv = p.h0 ? __ldg(p.h0 + (size_t)b * H + ug) : 0.f;
+        const float cv = p.c0 ? __ldg(p.c0 + (size_t)b * H + ug) : 0.f;
+        p.hs[(size_t)b * H + ug] = hv;
+        p.cs[(size_t)b * H + ug] = cv;
+        cst[sub] = cv;
+      }
+    }
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (w < PP_CELL_WARPS) {   // W_hh slice -> tensor memory (as in the single-tile kernel)
+    const int q = w & 3;
+    const float* wrow = p.whh + (size_t)(q * H + rank * 32 + lane) * H;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    __syncwarp();
+#pragma unroll 1
+    for (int ks = (w >> 2); ks < KS; ks += PP_CELL_WARPS / 4) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wrow + ks * 16 + i * 4));
+        split_pack2(v.x, v.y, hi[2 * i], lo[2 * i]);
+        split_pack2(v.z, v.w, hi[2 * i + 1], lo[2 * i + 1]);
+      }
+      tc::tmem_st_32x32b_x8(lane_base + SM::TM_A_HI + ks * 8, hi);
+      tc::tmem_st_32x32b_x8(lane_base + SM::TM_A_LO + ks * 8, lo);
+    }
+    tc::tmem_wait_st();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  cluster.sync();
+
+  const uint32_t hb_addr = tc::smem_u32(hb);
+  const size_t gstride = (size_t)4 * H;
+  const int n_iter = n_sub * S;
+
+  if (w_u == PP_CELL_WARPS) {
+    // ================= MMA warp =================
+    const uint32_t idesc = tc::make_idesc_bf16_f32(128, 16);
+    const uint64_t db0 = tc::make_smem_desc(hb_addr, 128, SM::RG_BYTES);
+    for (int k = 0; k < n_iter; ++k) {
+      const int sub = k % n_sub, s = k / n_sub;
+      const int cur = s & 1, nxt = cur ^ 1;
+      const int rg_valid = (sub_rows(sub) + 7) >> 3;
+      if (s + 1 < S && tc::elect_one())
+        tc::mbar_arrive_expect_tx(&h_full[sub * 2 + nxt], (uint32_t)(C * rg_valid * SM::SLICE));
+      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 0] = gtime();
+      if (s > 0 && !*dead) {
+        if (!tc::mbar_wait(&h_full[sub * 2 + cur], ((s - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 5); }
+      }
+      __syncwarp();
+      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 1] = gtime();
+      tc::fence_after_thread_sync();
+      if (tc::elect_one()) {
+        const uint64_t db_cur = db0 + (uint64_t)(((sub * 2 + cur) * SM::BUF_BYTES) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t ta_hi = tmem_base + SM::TM_A_HI + ks * 8, ta_lo = tmem_base + SM::TM_A_LO + ks * 8;
+          const uint64_t db_hi = db_cur + (uint64_t)(((ks >> 1) * SM::SLICE + (ks & 1) * 256) >> 4);
+          const uint64_t db_lo = db_hi + (uint64_t)(512 >> 4);
+          const uint32_t d = tmem_base + (sub * 4 + (ks % SM::NACC)) * 16;
+          tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks >= SM::NACC);
+          tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
+          tc::mma_bf16_ts(d, ta_hi, db_hi, idesc, true);
+        }
+        tc::mma_commit(&mma_done[sub]);
+      }
+      __syncwarp();
+      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 2] = gtime();
+    }
+  } else {
+    // ================= cell warps: warp w = row w of the current sub-tile, lane = hidden unit =================
+    const int rg = w >> 3, r8 = w & 7;
+    float gnext[4];
+    auto prefetch = [&](int k) {   // input projection of iteration k for this thread's element
+      const int sub = k % n_sub, s = k / n_sub, t = s / p.repeat;
+      const bool on = w < sub_rows(sub);
+      const int b = b0 + sub_row0(sub) + w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gnext[q] = on ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;
+    };
+    prefetch(0);
+    for (int k = 0; k < n_iter; ++k) {
+      const int sub = k % n_sub, s = k / n_sub, t = s / p.repeat;
+      const int nxt = (s & 1) ^ 1;
+      float gpre[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gpre[q] = gnext[q];
+      if (k + 1 < n_iter) prefetch(k + 1);
+      if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 5] = gtime();
+      if (!*dead) {
+        if (!tc::mbar_wait(&mma_done[sub], s & 1)) { *dead = 1; atomicExch(err, 6); }
+      }
+      if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 3] = gtime();
+      tc::fence_after_thread_sync();
+      __syncwarp();
+      float* gt = gt_all + (k & 1) * 16 * GT_LD;
+      if ((w >> 2) < 2) {   // 8 warps read the 128 x 16 accumulators: lane quarter w&3, 8-column block w>>2
+        const int q = w & 3, c0 = (w >> 2) * 8;
+        float v[8];
+        tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64 + c0), v);
+#pragma unroll
+        for (int a = 1; a < SM::NACC; ++a) {
+          float u[8];
+          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64 + a * 16 + c0), u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += u[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gt[(c0 + j) * GT_LD + q * 32 + lane] = v[j];
+      }
+      tc::fence_before_thread_sync();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 4] = gtime();
+
+      const int rows = sub_rows(sub);
+      const int rg_valid = (rows + 7) >> 3;
+      if (rg < rg_valid) {
+        unsigned char* hs_buf = hstage + ((sub * 2 + (s & 1)) * 2 + rg) * SM::SLICE;
+        __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+        if (w < rows) {
+          const int b = b0 + sub_row0(sub) + w;
+          const float* gr = gt + w * GT_LD + lane;
+          const float ig = fast_sigmoid(gr[0] + gpre[0]);
+          const float fg = fast_sigmoid(gr[32] + gpre[1]);
+          const float gg = fast_tanh(gr[64] + gpre[2]);
+          const float og = fast_sigmoid(gr[96] + gpre[3]);
+          const float cprev = sub == 0 ? cst[0] : cst[1];
+          const float cn = fg * cprev + ig * gg;
+          const float hn = og * fast_tanh(cn);
+          if (sub == 0) cst[0] = cn; else cst[1] = cn;
+          float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
+          go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
+          p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
+          p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
+          if (p.head_in && (s % p.repeat) == p.repeat - 1)
+            p.head_in[((size_t)t * B + b) * H + ug] = fast_tanh(hn);
+          split_bf16(hn, hi, lo);
+        }
+        unsigned char* dst = hs_buf + (lane >> 3) * 128 + r8 * 16 + (lane & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(dst + 512) = lo;
+        tc::fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 256;" ::"r"(2 + rg) : "memory");   // the 8 warps of this row group
+        if (s + 1 < S && r8 < C && tc::elect_one()) {
+          const uint32_t d = r8;
+          const uint32_t dst_local = hb_addr + (sub * 2 + nxt) * SM::BUF_BYTES + rg * SM::RG_BYTES + rank * SM::SLICE;
+          tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf), SM::SLICE,
+                                   tc::mapa(tc::smem_u32(&h_full[sub * 2 + nxt]), d));
+        }
+      }
+      if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 7] = gtime();
+    }
+  }
+  tc::fence_before_thread_sync();
+  cluster.sync();
+  if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, SM::TM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
 template <int H, int NB>
@@ -524,12 +768,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, SM::TM_COLS); }
 }
 
+bool scan_pingpong_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("R2D2_SCAN_PINGPONG"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 template <typename Kern, typename Params>
-int launch_cluster_tc(Kern kern, const Params& p, int cluster_size, int n_clusters, int smem_bytes, cudaStream_t stream) {
+int launch_cluster_tc(Kern kern, const Params& p, int cluster_size, int n_clusters, int smem_bytes, cudaStream_t stream,
+                      int threads = TC_THREADS) {
   R2D2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cluster_size * n_clusters);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -593,6 +844,8 @@ int fwd_tc(const ScanFwdParams& p_in, cudaStream_t stream) {
   p.rows_per_cluster = t.rows_per_cluster;
   if (t.nb == 16)
     return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 16>, p, H / 32, t.n_clusters, TcFwdSmem<H, 16>::BYTES, stream);
+  if (scan_pingpong_enabled())
+    return launch_cluster_tc(lstm_scan_fwd_pp_kernel<H>, p, H / 32, t.n_clusters, PpFwdSmem<H>::BYTES, stream, PP_THREADS);
   return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 32>, p, H / 32, t.n_clusters, TcFwdSmem<H, 32>::BYTES, stream);
 }
 template <int H>
