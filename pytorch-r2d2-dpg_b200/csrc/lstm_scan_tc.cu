@@ -438,22 +438,23 @@ __global__ void __launch_bounds__(PP_THREADS, 1) lstm_scan_fwd_pp_kernel(ScanFwd
   } else {
     // ================= cell warps: warp w = row w of the current sub-tile, lane = hidden unit =================
     const int rg = w >> 3, r8 = w & 7;
-    float gnext[4];
-    auto prefetch = [&](int k) {   // input projection of iteration k for this thread's element
+    float gq0[4], gq1[4];   // input projections of the next two iterations (prefetch distance 2: ~2 us of HBM latency cover)
+    auto prefetch = [&](int k, float (&dst)[4]) {
       const int sub = k % n_sub, s = k / n_sub, t = s / p.repeat;
-      const bool on = w < sub_rows(sub);
+      const bool on = k < n_iter && w < sub_rows(sub);
       const int b = b0 + sub_row0(sub) + w;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) gnext[q] = on ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;
+      for (int q = 0; q < 4; ++q) dst[q] = on ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;
     };
-    prefetch(0);
+    prefetch(0, gq0);
+    prefetch(1, gq1);
     for (int k = 0; k < n_iter; ++k) {
       const int sub = k % n_sub, s = k / n_sub, t = s / p.repeat;
       const int nxt = (s & 1) ^ 1;
       float gpre[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) gpre[q] = gnext[q];
-      if (k + 1 < n_iter) prefetch(k + 1);
+      for (int q = 0; q < 4; ++q) { gpre[q] = gq0[q]; gq0[q] = gq1[q]; }
+      prefetch(k + 2, gq1);
       if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 5] = gtime();
       if (!*dead) {
         if (!tc::mbar_wait(&mma_done[sub], s & 1)) { *dead = 1; atomicExch(err, 6); }
@@ -485,23 +486,18 @@ __global__ void __launch_bounds__(PP_THREADS, 1) lstm_scan_fwd_pp_kernel(ScanFwd
       if (rg < rg_valid) {
         unsigned char* hs_buf = hstage + ((sub * 2 + (s & 1)) * 2 + rg) * SM::SLICE;
         __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
-        if (w < rows) {
-          const int b = b0 + sub_row0(sub) + w;
+        float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cn = 0.f, hn = 0.f;
+        const bool on = w < rows;
+        if (on) {
           const float* gr = gt + w * GT_LD + lane;
-          const float ig = fast_sigmoid(gr[0] + gpre[0]);
-          const float fg = fast_sigmoid(gr[32] + gpre[1]);
-          const float gg = fast_tanh(gr[64] + gpre[2]);
-          const float og = fast_sigmoid(gr[96] + gpre[3]);
+          ig = fast_sigmoid(gr[0] + gpre[0]);
+          fg = fast_sigmoid(gr[32] + gpre[1]);
+          gg = fast_tanh(gr[64] + gpre[2]);
+          og = fast_sigmoid(gr[96] + gpre[3]);
           const float cprev = sub == 0 ? cst[0] : cst[1];
-          const float cn = fg * cprev + ig * gg;
-          const float hn = og * fast_tanh(cn);
+          cn = fg * cprev + ig * gg;
+          hn = og * fast_tanh(cn);
           if (sub == 0) cst[0] = cn; else cst[1] = cn;
-          float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
-          go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
-          p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
-          p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
-          if (p.head_in && (s % p.repeat) == p.repeat - 1)
-            p.head_in[((size_t)t * B + b) * H + ug] = fast_tanh(hn);
           split_bf16(hn, hi, lo);
         }
         unsigned char* dst = hs_buf + (lane >> 3) * 128 + r8 * 16 + (lane & 7) * 2;
@@ -514,6 +510,15 @@ __global__ void __launch_bounds__(PP_THREADS, 1) lstm_scan_fwd_pp_kernel(ScanFwd
           const uint32_t dst_local = hb_addr + (sub * 2 + nxt) * SM::BUF_BYTES + rg * SM::RG_BYTES + rank * SM::SLICE;
           tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf), SM::SLICE,
                                    tc::mapa(tc::smem_u32(&h_full[sub * 2 + nxt]), d));
+        }
+        if (on) {   // the saved activations leave AFTER the exchange has been started: they are off the serial chain
+          const int b = b0 + sub_row0(sub) + w;
+          float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
+          go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
+          p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
+          p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
+          if (p.head_in && (s % p.repeat) == p.repeat - 1)
+            p.head_in[((size_t)t * B + b) * H + ug] = fast_tanh(hn);
         }
       }
       if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 7] = gtime();
