@@ -244,21 +244,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
       if (e < n_rg_valid) {
         const int n = 8 * e + r8, b = b0 + n;
         __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
-        if (b < b_end) {
+        float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cn = 0.f, hn = 0.f;
+        const bool on = b < b_end;
+        if (on) {
           const float* gr = gt + n * GT_LD + lane;
-          const float ig = fast_sigmoid(gr[0] + gpre[j][0]);
-          const float fg = fast_sigmoid(gr[32] + gpre[j][1]);
-          const float gg = fast_tanh(gr[64] + gpre[j][2]);
-          const float og = fast_sigmoid(gr[96] + gpre[j][3]);
-          const float cn = fg * cst[j] + ig * gg;
-          const float hn = og * fast_tanh(cn);
+          ig = fast_sigmoid(gr[0] + gpre[j][0]);
+          fg = fast_sigmoid(gr[32] + gpre[j][1]);
+          gg = fast_tanh(gr[64] + gpre[j][2]);
+          og = fast_sigmoid(gr[96] + gpre[j][3]);
+          cn = fg * cst[j] + ig * gg;
+          hn = og * fast_tanh(cn);
           cst[j] = cn;
-          float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
-          go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
-          p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
-          p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
-          if (p.head_in && (s % p.repeat) == p.repeat - 1)
-            p.head_in[((size_t)t * B + b) * H + ug] = fast_tanh(hn);
           split_bf16(hn, hi, lo);
         }
         unsigned char* dst = hs_buf + e * SM::SLICE + (lane >> 3) * 128 + r8 * 16 + (lane & 7) * 2;  // [plane][chunk][row][8]
@@ -271,6 +267,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
           const uint32_t dst_local = hb_addr + nxt * SM::BUF_BYTES + e * SM::RG_BYTES + rank * SM::SLICE;
           tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf + e * SM::SLICE), SM::SLICE,
                                    tc::mapa(tc::smem_u32(&h_full[nxt]), d));
+        }
+        if (on) {   // saved activations leave after the exchange has been started: off the serial chain
+          float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
+          go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
+          p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
+          p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
+          if (p.head_in && (s % p.repeat) == p.repeat - 1)
+            p.head_in[((size_t)t * B + b) * H + ug] = fast_tanh(hn);
         }
       }
     }
@@ -662,12 +666,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       if (!tc::mbar_wait(&ps_full[buf], ((it - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 3); }
     }
 
-    // ---- pointwise backward of the cell (thread = (unit = lane, row r8 of row group e))
+    // ---- pointwise backward of the cell (thread = (unit = lane, row r8 of row group e)); the dG values go to the MMA
+    // operand tile first - their HBM copies are written below, after the tensor-core step has been started
+    float dgr[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int n = 8 * (half + 2 * j) + r8, b = b0 + n;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dgr[j][q] = 0.f;
       if (b < b_end) {
-        float dg[4];
         float dh = phead[j];
         if (it > 0) {
 #pragma unroll
@@ -676,33 +683,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
         const float ig = pg[j][0], fg = pg[j][1], gg = pg[j][2], og = pg[j][3];
         const float tcn = fast_tanh(pc_new[j]);
         const float dc = dcn[j] + dh * og * (1.f - tcn * tcn);
-        dg[3] = dh * tcn * og * (1.f - og);
-        dg[0] = dc * gg * ig * (1.f - ig);
-        dg[1] = dc * pc_prev[j] * fg * (1.f - fg);
-        dg[2] = dc * ig * (1.f - gg * gg);
+        dgr[j][3] = dh * tcn * og * (1.f - og);
+        dgr[j][0] = dc * gg * ig * (1.f - ig);
+        dgr[j][1] = dc * pc_prev[j] * fg * (1.f - fg);
+        dgr[j][2] = dc * ig * (1.f - gg * gg);
         dcn[j] = dc * fg;
-        float* go = p.dgates + ((size_t)s * B + b) * gstride + ug;
-        go[0] = dg[0]; go[H] = dg[1]; go[2 * H] = dg[2]; go[3 * H] = dg[3];
-        if (p.repeat > 1) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) keep[j][q] += dg[q];
-          if (s % p.repeat == 0) {
-            float* gi = p.dgin + ((size_t)t * B + b) * gstride + ug;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { gi[q * H] = keep[j][q]; keep[j][q] = 0.f; }
-          }
-        }
         // operand tile of the MMA: K index r = q*32 + lane -> chunk (q*4 + lane/8), element lane%8
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           __nv_bfloat16 hi, lo;
-          split_bf16(dg[q], hi, lo);
+          split_bf16(dgr[j][q], hi, lo);
           const int off = ((q * 4 + (lane >> 3)) * NB + n) * 16 + (lane & 7) * 2;
           *reinterpret_cast<__nv_bfloat16*>(dgs + off) = hi;
           *reinterpret_cast<__nv_bfloat16*>(dgs + SM::DG_PLANE + off) = lo;
         }
       }
     }
+    auto store_dg = [&]() {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int b = b0 + 8 * (half + 2 * j) + r8;
+        if (b < b_end) {
+          float* go = p.dgates + ((size_t)s * B + b) * gstride + ug;
+          go[0] = dgr[j][0]; go[H] = dgr[j][1]; go[2 * H] = dgr[j][2]; go[3 * H] = dgr[j][3];
+          if (p.repeat > 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) keep[j][q] += dgr[j][q];
+            if (s % p.repeat == 0) {
+              float* gi = p.dgin + ((size_t)t * B + b) * gstride + ug;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { gi[q * H] = keep[j][q]; keep[j][q] = 0.f; }
+            }
+          }
+        }
+      }
+    };
+    if (s == 0) store_dg();
     if (s == 0) break;  // dh_{-1} is not needed: the initial state is data, not a parameter
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
@@ -730,6 +746,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       }
       __syncwarp();
     }
+    store_dg();   // HBM copies of dG (and the per-row dgin sums) overlap with the tensor-core step
     if (!*dead) {
       if (!tc::mbar_wait(mma_done, it & 1)) { *dead = 1; atomicExch(err, 4); }
     }
