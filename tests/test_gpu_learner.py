@@ -101,6 +101,32 @@ def test_cfg2_full_size_against_port(eng_mod):
         print(f"cfg-2 iteration {it}: worst relative error {max(errs.values()):.3e}")
 
 
+def test_cfg3_shape_generic_hidden_512(eng_mod):
+    """BASELINE.json configs[2] shape (obs=376 act=17 hidden=512 seq_len=80 burn_in=40) at a reduced batch: hidden 512 is
+    outside the cluster kernels (4 MB of bf16x3 W_hh does not fit a cluster) and takes the generic per-step path."""
+    pc = ref_port.PathConfig(obs=376, act=17, hidden=512, batch=24, burn_in=40, learning=80, n_step=5)
+    torch.set_num_threads(max(1, min(32, torch.get_num_threads())))
+    port = ref_port.PortLearner(pc, seed=2)
+    cfg = eng_mod.PathConfig(obs=376, act=17, hidden=512, batch=24, burn_in=40, learning=80, n_step=5)
+    eng = eng_mod.LearnerEngine(cfg)
+    sd = lambda m: {k: v.detach().numpy() for k, v in m.state_dict().items()}  # noqa: E731
+    eng.load_state_dicts(sd(port.actor), sd(port.critic))
+    batch = ref_port.synthetic_batch(pc, seed=4)
+    ref = port.iteration(batch)
+    eng.set_batch(batch)
+    eng.step()
+    torch.cuda.synchronize()
+    errs = {"q": rel_l2(eng.q_value.cpu().numpy(), ref["q_value"]),
+            "target": rel_l2(eng.target_q_value.cpu().numpy(), ref["target_q_value"]),
+            "prio": rel_l2(eng.priority.cpu().numpy(), ref["priority"])}
+    for net in ("actor", "critic"):
+        gr = flat_sd(eng.views(net, "grads"))
+        for k in eng_mod.PARAM_KEYS:
+            errs[f"{net}_grad/{k}"] = rel_l2(gr[k], ref[f"{net}_grad"][k])
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
+
+
 def test_hard_target_update(eng_mod):
     cfg = eng_mod.PathConfig(obs=5, act=2, hidden=32, batch=4, burn_in=3, learning=4, n_step=2, target_interval=2)
     pc = ref_port.PathConfig(obs=5, act=2, hidden=32, batch=4, burn_in=3, learning=4, n_step=2, target_interval=2)
