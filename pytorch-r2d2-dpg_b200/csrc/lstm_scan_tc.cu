@@ -28,6 +28,9 @@ int* scan_error_flag();  // device int, 0 = ok (defined below)
 namespace {
 
 constexpr int TC_THREADS = 512, TC_WARPS = 16;
+#ifndef R2D2_SCAN_NACC
+#define R2D2_SCAN_NACC 4   // independent TMEM accumulators per tile (summed in the epilogue)
+#endif
 constexpr int GT_LD = 128 + 4;
 
 // Cell non-linearities on the serial chain: exp via MUFU.EX2 (__expf, ~2 ulp) and an approximate reciprocal
@@ -65,7 +68,7 @@ struct TcFwdSmem {
   static constexpr int OFF_HB = 0;
   // tensor memory columns: NACC independent accumulators D_a at [a*NB, ..), then the W_hh slice: hi plane at 128
   // (H/2 columns: two bf16 per column), lo plane after it
-  static constexpr int NACC = (H / 16) < 4 ? (H / 16) : 4;
+  static constexpr int NACC = (H / 16) < R2D2_SCAN_NACC ? (H / 16) : R2D2_SCAN_NACC;
   static constexpr int TM_A_HI = 128, TM_A_LO = 128 + H / 2, TM_COLS = 512;
   static constexpr int OFF_GT = OFF_HB + 2 * BUF_BYTES;            // fp32 [NB][GT_LD]
   static constexpr int OFF_HSTAGE = OFF_GT + NB * GT_LD * 4;       // [dbuf][row group][plane][4 chunks][8][16 B]
@@ -300,7 +303,7 @@ struct PpFwdSmem {
   static constexpr int RG_BYTES = C * SLICE;
   static constexpr int BUF_BYTES = 2 * RG_BYTES;          // 16 rows
   static constexpr int OFF_HB = 0;                        // [sub][buf][row group][slice][plane][4 chunks][8][16 B]
-  static constexpr int NACC = (H / 16) < 4 ? (H / 16) : 4;
+  static constexpr int NACC = (H / 16) < R2D2_SCAN_NACC ? (H / 16) : R2D2_SCAN_NACC;
   static constexpr int TM_A_HI = 128, TM_A_LO = 128 + H / 2, TM_COLS = 512;   // D[sub][acc] at (sub*4 + acc)*16
   static constexpr int OFF_GT = OFF_HB + 4 * BUF_BYTES;   // fp32 [2 (iteration parity)][16][GT_LD]
   static constexpr int OFF_HSTAGE = OFF_GT + 2 * 16 * GT_LD * 4;   // [sub][step parity][row group][SLICE]
@@ -545,7 +548,7 @@ struct TcBwdSmem {
   static constexpr int OFF_DG = 0;                                // [plane]
   // tensor memory: NACC independent accumulators per M tile, D_(mt,a) at [(mt*NACC + a)*NB, ..); W^T tiles from
   // column 256: (mt, plane) -> 256 + (2 mt + plane) * 64
-  static constexpr int NACC = 4;
+  static constexpr int NACC = R2D2_SCAN_NACC;
   static constexpr int TM_A = 256, TM_COLS = 512;
   static_assert(MT * NACC * NB <= 256, "accumulators overlap the weight tiles in tensor memory");
   static constexpr int OFF_PS = OFF_DG + 2 * DG_PLANE;            // [buf][src][n][32]
