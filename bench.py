@@ -185,7 +185,7 @@ def run_reference(args, c):
                                        f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)"},
             "e2e": {"value": value, "unit": "seq-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 _REAL_STDOUT = None
