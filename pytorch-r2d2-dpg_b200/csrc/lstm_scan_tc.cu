@@ -29,7 +29,7 @@ namespace {
 
 constexpr int TC_THREADS = 512, TC_WARPS = 16;
 #ifndef R2D2_SCAN_NACC
-#define R2D2_SCAN_NACC 4   // independent TMEM accumulators per tile (summed in the epilogue)
+#define R2D2_SCAN_NACC 1   // TMEM accumulators per tile (>1: independent chains summed in the epilogue; measured: no gain, 4x the tcgen05.ld traffic)
 #endif
 constexpr int GT_LD = 128 + 4;
 

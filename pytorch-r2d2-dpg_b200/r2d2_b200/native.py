@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libr2d2_b200.so")
+LIB_PATH = os.environ.get("R2D2_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libr2d2_b200.so")  # env: dev builds
 
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 EPI_NONE, EPI_TANH, EPI_MUL_DTANH, EPI_ADD_Z = 0, 1, 2, 3
