@@ -360,7 +360,7 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "lstm_scan_fwd_tc_kernel (persistent cluster LSTM scan, tcgen05, W_hh in TMEM, %d cell steps)" % S, "bound": "tensor",
+    roofline = {"kernel": "lstm_scan_fwd_pp_kernel (persistent cluster LSTM scan, tcgen05 ping-pong over two row sub-tiles, W_hh in TMEM, %d cell steps)" % S, "bound": "tensor",
                 "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
                 "traffic": traffic, "peak_source": peaks["source"] + " bf16 dense burst (kernel timed alone)",
                 "us_per_step": scan_ms * 1e3 / S,
