@@ -283,6 +283,11 @@ int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   // skinny problems (K < 64: obs/act inputs; N < 32: heads, dW1/dW3 blocks) are launch/latency bound: the single-launch
   // mma.sync kernel beats pack + pack + tcgen05 there (tools/gemm_bench.py); everything else goes to the tcgen05 path
   const bool skinny = (p.K + p.K2 < 64) || (p.N < 32) || (p.M < 32);
+  if (gemm_get_impl() == 1 && gemm_get_impl_skinny_mma()) {   // default mode: degenerate shapes -> fp32 streaming kernels
+    bool handled = false;
+    R2D2_TRY(gemm_thin_try(p, layout, stream, &handled));
+    if (handled) return R2D2_OK;
+  }
   if (gemm_get_impl() == 1 && !(skinny && gemm_get_impl_skinny_mma())) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("R2D2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }

@@ -32,6 +32,8 @@ struct GemmParams {
   const float* Z = nullptr;  long long ldz = 0;   // [M,N] aux for the epilogue
   int epilogue = EPI_NONE;
   int split_k = 1;           // >1: partial products are atomically added into C (C must be pre-zeroed)
+  int reuse_packed_a = 0;    // tcgen05 path: A (pointer, shape, layout) is the operand the previous gemm_f32 call packed
+                             // and its contents have not changed since -> skip the pack pass (dW_hh then dW_ih of a chain)
   int debug_flags = 0;       // dev only (env R2D2_GEMM_DEBUG): 1 = producers skip fetch+convert, 2 = skip MMAs, 4 = skip epilogue stores
 };
 
@@ -46,6 +48,9 @@ int gemm_get_impl();
 void gemm_set_impl_skinny_mma(int on);
 int gemm_get_impl_skinny_mma();
 int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream);
+// fp32 streaming kernels for contractions with one dimension <= 32 (gemm_thin.cu); *handled = false when the shape is
+// not one of theirs
+int gemm_thin_try(const GemmParams& p, GemmLayout layout, cudaStream_t stream, bool* handled);
 int gemm_tc_suggest_split_k(int M, int N, int K);
 
 }  // namespace r2d2

@@ -1,0 +1,294 @@
+// Degenerate contractions of the learner path as plain fp32 FMA kernels.
+//
+// A third of the GEMM launches of one iteration have a dimension of 6..23 (obs / action widths, models.py:17-19,
+// :62-64): x*W1^T (K = 17 | 17+6), the heads (N = 6), their dgrads and the dW1 / dW3 blocks.  On a 128-wide tensor
+// core tile they are >90% padding and ran at 16-36 us each (profiles/r01_summary.md) although they only stream
+// 2-32 MB.  Here every one is a single HBM-bound pass in exact fp32:
+//   thin_smallk : C[M,N] = epi(A[M,K] W (+ A2[M,K2] W2) + bias),  K + K2 <= 32   (NT / NN)
+//   thin_smalln : C[M,N] = epi(A[M,K] W + bias),                  N <= 32        (NT / NN)
+//   thin_tn     : C[M,N] += A[K,M]^T B[K,N],                      M <= 32 or N <= 32, reduction over K rows
+#include "gemm.cuh"
+#include "tc05.cuh"
+
+namespace r2d2 {
+namespace {
+
+__device__ __forceinline__ float apply_epilogue(float v, int epilogue, float z) {
+  if (epilogue == EPI_TANH) return tc::tanh_fast(v);
+  if (epilogue == EPI_MUL_DTANH) return v * (1.f - z * z);
+  if (epilogue == EPI_ADD_Z) return v + z;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small K.  Block = 256 threads = 32 rows x 256 columns per pass (thread: 8 rows x 4 columns), W resident in shared
+// memory for the whole (persistent) block, A rows staged per pass.
+// ------------------------------------------------------------------------------------------------
+constexpr int SK_ROWS = 32, SK_COLS = 256, SK_KMAX = 32, SK_THREADS = 256;
+
+template <bool NN>
+__global__ void __launch_bounds__(SK_THREADS) thin_smallk_kernel(GemmParams p, int vec_c, int vec_z) {
+  __shared__ __align__(16) float Ws[SK_KMAX][SK_COLS];
+  __shared__ __align__(16) float As[SK_ROWS][SK_KMAX];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.y * SK_COLS;
+  const int Kt = p.K + p.K2;
+  for (int idx = tid; idx < SK_KMAX * SK_COLS; idx += SK_THREADS) {
+    const int k = idx / SK_COLS, n = n0 + idx % SK_COLS;
+    float v = 0.f;
+    if (n < p.N && k < Kt) {
+      if (NN) v = __ldg(p.B + (long long)k * p.ldb + n);
+      else    v = (k < p.K) ? __ldg(p.B + (long long)n * p.ldb + k) : __ldg(p.B2 + (long long)n * p.ldb2 + (k - p.K));
+    }
+    Ws[k][idx % SK_COLS] = v;
+  }
+  const int cg = tid & 63, rgp = tid >> 6;
+  const int col = n0 + cg * 4;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (col + j < p.N) bias[j] = __ldg(p.bias + col + j);
+  }
+  const int k4n = (Kt + 3) >> 2;
+  const int row_tiles = (p.M + SK_ROWS - 1) / SK_ROWS;
+  for (int rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
+    const int r0 = rt * SK_ROWS;
+    __syncthreads();   // previous pass done with As (and, first time, Ws complete)
+    for (int idx = tid; idx < SK_ROWS * SK_KMAX; idx += SK_THREADS) {
+      const int r = idx / SK_KMAX, k = idx % SK_KMAX, row = r0 + r;
+      float v = 0.f;
+      if (row < p.M && k < Kt)
+        v = (k < p.K) ? __ldg(p.A + (long long)row * p.lda + k) : __ldg(p.A2 + (long long)row * p.lda2 + (k - p.K));
+      As[r][k] = v;
+    }
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[r][j] = bias[j];
+    for (int k4 = 0; k4 < k4n; ++k4) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[4 * k4 + 0][cg * 4]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&Ws[4 * k4 + 1][cg * 4]);
+      const float4 w2 = *reinterpret_cast<const float4*>(&Ws[4 * k4 + 2][cg * 4]);
+      const float4 w3 = *reinterpret_cast<const float4*>(&Ws[4 * k4 + 3][cg * 4]);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[rgp * 8 + r][4 * k4]);
+        acc[r][0] += a.x * w0.x + a.y * w1.x + a.z * w2.x + a.w * w3.x;
+        acc[r][1] += a.x * w0.y + a.y * w1.y + a.z * w2.y + a.w * w3.y;
+        acc[r][2] += a.x * w0.z + a.y * w1.z + a.z * w2.z + a.w * w3.z;
+        acc[r][3] += a.x * w0.w + a.y * w1.w + a.z * w2.w + a.w * w3.w;
+      }
+    }
+    if (col >= p.N) continue;
+    const bool full = col + 3 < p.N;
+    const bool needs_z = p.epilogue == EPI_MUL_DTANH || p.epilogue == EPI_ADD_Z;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int row = r0 + rgp * 8 + r;
+      if (row >= p.M) break;
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (needs_z) {
+        const float* zp = p.Z + (long long)row * p.ldz + col;
+        if (full && vec_z) { const float4 t = *reinterpret_cast<const float4*>(zp); z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w; }
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (col + j < p.N) z[j] = zp[j];
+        }
+      }
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = apply_epilogue(acc[r][j], p.epilogue, z[j]);
+      float* cp = p.C + (long long)row * p.ldc + col;
+      if (full && vec_c) *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (col + j < p.N) cp[j] = v[j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small N.  One warp per pair of rows; lane owns the k slices {128 j + 4 lane .. +3}; W^T[n][k] in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int SN_THREADS = 256;
+
+template <bool NN, int NP>
+__global__ void __launch_bounds__(SN_THREADS) thin_smalln_kernel(GemmParams p, int kpad) {
+  extern __shared__ __align__(16) float Wt[];   // [NP][kpad]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < NP * kpad; idx += SN_THREADS) {
+    int n, k;
+    if (NN) { k = idx / NP; n = idx % NP; } else { n = idx / kpad; k = idx % kpad; }
+    float v = 0.f;
+    if (n < p.N && k < p.K) v = NN ? __ldg(p.B + (long long)k * p.ldb + n) : __ldg(p.B + (long long)n * p.ldb + k);
+    Wt[n * kpad + k] = v;
+  }
+  __syncthreads();
+  const int kchunks = kpad >> 7;
+  const int pairs = (p.M + 1) >> 1;
+  const bool needs_z = p.epilogue == EPI_MUL_DTANH || p.epilogue == EPI_ADD_Z;
+  for (int pr = blockIdx.x * (SN_THREADS / 32) + warp; pr < pairs; pr += gridDim.x * (SN_THREADS / 32)) {
+    const int row0 = 2 * pr, row1 = row0 + 1;
+    const bool has1 = row1 < p.M;
+    float acc0[NP], acc1[NP];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) { acc0[n] = 0.f; acc1[n] = 0.f; }
+    for (int j = 0; j < kchunks; ++j) {
+      const int k = j * 128 + lane * 4;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+      if (k < p.K) {   // K % 4 == 0 is a dispatch precondition
+        a0 = __ldg(reinterpret_cast<const float4*>(p.A + (long long)row0 * p.lda + k));
+        if (has1) a1 = __ldg(reinterpret_cast<const float4*>(p.A + (long long)row1 * p.lda + k));
+      }
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const float4 w = *reinterpret_cast<const float4*>(&Wt[n * kpad + k]);
+        acc0[n] += a0.x * w.x + a0.y * w.y + a0.z * w.z + a0.w * w.w;
+        acc1[n] += a1.x * w.x + a1.y * w.y + a1.z * w.z + a1.w * w.w;
+      }
+    }
+    float out0 = 0.f, out1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NP; ++n) {
+      const float s0 = warp_sum(acc0[n]), s1 = warp_sum(acc1[n]);
+      if (lane == n) { out0 = s0; out1 = s1; }
+    }
+    if (lane < p.N) {
+      const float b = p.bias ? __ldg(p.bias + lane) : 0.f;
+      const float z0 = needs_z ? p.Z[(long long)row0 * p.ldz + lane] : 0.f;
+      p.C[(long long)row0 * p.ldc + lane] = apply_epilogue(out0 + b, p.epilogue, z0);
+      if (has1) {
+        const float z1 = needs_z ? p.Z[(long long)row1 * p.ldz + lane] : 0.f;
+        p.C[(long long)row1 * p.ldc + lane] = apply_epilogue(out1 + b, p.epilogue, z1);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TN with one small output dimension: X[K rows][P] is the wide operand (thread = one of its columns), Y[K rows][Q<=32]
+// the narrow one (staged per 128-row chunk in shared memory, read as broadcast float4).  Accumulates into C with
+// atomics once per block (split-K contract of gemm_f32: C pre-zeroed by the caller).
+// ------------------------------------------------------------------------------------------------
+constexpr int TN_THREADS = 256, TN_CHUNK = 128;
+
+template <int QP>
+__global__ void __launch_bounds__(TN_THREADS) thin_tn_kernel(const float* __restrict__ X, long long ldx, int P,
+                                                             const float* __restrict__ Y, long long ldy, int Q, int K,
+                                                             float* __restrict__ C, long long ldc, int small_is_m) {
+  __shared__ __align__(16) float Ys[TN_CHUNK][QP];
+  const int tid = threadIdx.x;
+  const int pc = blockIdx.y * TN_THREADS + tid;
+  const bool pon = pc < P;
+  float acc[QP];
+#pragma unroll
+  for (int q = 0; q < QP; ++q) acc[q] = 0.f;
+  const int chunks = (K + TN_CHUNK - 1) / TN_CHUNK;
+  for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+    const int r0 = ch * TN_CHUNK;
+    const int nr = min(TN_CHUNK, K - r0);
+    __syncthreads();
+    for (int idx = tid; idx < TN_CHUNK * QP; idx += TN_THREADS) {
+      const int r = idx / QP, q = idx % QP;
+      Ys[r][q] = (r < nr && q < Q) ? __ldg(Y + (long long)(r0 + r) * ldy + q) : 0.f;
+    }
+    __syncthreads();
+    const float* xp = X + (long long)r0 * ldx + pc;
+#pragma unroll 4
+    for (int r = 0; r < nr; ++r) {
+      const float x = pon ? __ldg(xp + (long long)r * ldx) : 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < QP / 4; ++q4) {
+        const float4 y = *reinterpret_cast<const float4*>(&Ys[r][q4 * 4]);
+        acc[q4 * 4 + 0] += x * y.x; acc[q4 * 4 + 1] += x * y.y; acc[q4 * 4 + 2] += x * y.z; acc[q4 * 4 + 3] += x * y.w;
+      }
+    }
+  }
+  if (!pon) return;
+#pragma unroll
+  for (int q = 0; q < QP; ++q) {
+    if (q < Q) atomicAdd(small_is_m ? C + (long long)q * ldc + pc : C + (long long)pc * ldc + q, acc[q]);
+  }
+}
+
+bool aligned16(const float* ptr, long long ld) {
+  return ptr != nullptr && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && (ld % 4 == 0);
+}
+
+template <int QP>
+int launch_thin_tn(const float* X, long long ldx, int P, const float* Y, long long ldy, int Q, int K, float* C,
+                   long long ldc, int small_is_m, cudaStream_t stream) {
+  const int chunks = ceil_div(K, TN_CHUNK), py = ceil_div(P, TN_THREADS);
+  int gx = chunks < 296 / py ? chunks : 296 / py;
+  if (gx < 1) gx = 1;
+  thin_tn_kernel<QP><<<dim3(gx, py), TN_THREADS, 0, stream>>>(X, ldx, P, Y, ldy, Q, K, C, ldc, small_is_m);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+template <bool NN, int NP>
+int launch_thin_smalln(const GemmParams& p, cudaStream_t stream) {
+  const int kpad = ceil_div(p.K, 128) * 128;
+  const size_t smem = (size_t)NP * kpad * sizeof(float);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    R2D2_CUDA_TRY(cudaFuncSetAttribute(thin_smalln_kernel<NN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int pairs = (p.M + 1) / 2;
+  int grid = ceil_div(pairs, SN_THREADS / 32);
+  if (grid > 148 * 4) grid = 148 * 4;
+  thin_smalln_kernel<NN, NP><<<grid, SN_THREADS, smem, stream>>>(p, kpad);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+}  // namespace
+
+// returns R2D2_OK and sets *handled when one of the thin kernels took the problem
+int gemm_thin_try(const GemmParams& p, GemmLayout layout, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if (layout == GEMM_TN) {
+    if (p.split_k <= 1 || p.K2 != 0) return R2D2_OK;          // accumulate-into-zeroed-C contract only
+    const bool m_small = p.M <= 32, n_small = p.N <= 32;
+    if (!m_small && !n_small) return R2D2_OK;
+    // C[m][n] = sum_r A[r][m] B[r][n]
+    const bool small_is_m = m_small && (!n_small || p.M <= p.N);
+    const float* X = small_is_m ? p.B : p.A;  const long long ldx = small_is_m ? p.ldb : p.lda;
+    const float* Y = small_is_m ? p.A : p.B;  const long long ldy = small_is_m ? p.lda : p.ldb;
+    const int P = small_is_m ? p.N : p.M, Q = small_is_m ? p.M : p.N;
+    *handled = true;
+    if (Q <= 8)  return launch_thin_tn<8>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, stream);
+    if (Q <= 16) return launch_thin_tn<16>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, stream);
+    if (Q <= 24) return launch_thin_tn<24>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, stream);
+    return launch_thin_tn<32>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, stream);
+  }
+  if (p.split_k != 1) return R2D2_OK;
+  const bool nn = layout == GEMM_NN;
+  if (p.N <= 32 && p.K2 == 0 && p.K >= 64 && p.K <= 2048 && (p.K % 4 == 0) && aligned16(p.A, p.lda)) {
+    *handled = true;
+    if (p.N <= 8)  return nn ? launch_thin_smalln<true, 8>(p, stream) : launch_thin_smalln<false, 8>(p, stream);
+    if (p.N <= 16) return nn ? launch_thin_smalln<true, 16>(p, stream) : launch_thin_smalln<false, 16>(p, stream);
+    return nn ? launch_thin_smalln<true, 32>(p, stream) : launch_thin_smalln<false, 32>(p, stream);
+  }
+  if (p.K + p.K2 <= SK_KMAX && (p.K2 == 0 || !nn)) {
+    *handled = true;
+    const int row_tiles = ceil_div(p.M, SK_ROWS), ny = ceil_div(p.N, SK_COLS);
+    int gx = row_tiles < 444 / ny ? row_tiles : 444 / ny;
+    if (gx < 1) gx = 1;
+    const int vec_c = aligned16(p.C, p.ldc) ? 1 : 0, vec_z = aligned16(p.Z, p.ldz) ? 1 : 0;
+    if (nn) thin_smallk_kernel<true><<<dim3(gx, ny), SK_THREADS, 0, stream>>>(p, vec_c, vec_z);
+    else    thin_smallk_kernel<false><<<dim3(gx, ny), SK_THREADS, 0, stream>>>(p, vec_c, vec_z);
+    count_launch();
+    R2D2_CUDA_TRY(cudaGetLastError());
+    return R2D2_OK;
+  }
+  return R2D2_OK;
+}
+
+}  // namespace r2d2

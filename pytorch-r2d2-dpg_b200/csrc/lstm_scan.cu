@@ -13,6 +13,7 @@
 
 #include "gemm.cuh"
 #include "lstm_scan.cuh"
+#include "elementwise.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -564,15 +565,21 @@ int lstm_scan_backward(const ScanBwdParams& p, cudaStream_t stream) {
   R2D2_REQUIRE(p.gates && p.hs && p.cs && p.whh && p.dgates, "null pointer");
   R2D2_REQUIRE(p.T > 0 && p.B > 0 && p.H > 0 && p.repeat >= 1, "shape");
   R2D2_REQUIRE(p.repeat == 1 || (p.dgin && p.dgin != p.dgates), "dgin buffer required when repeat > 1");
-  if (lstm_scan_cluster_supported(p.H) && lstm_scan_get_impl() == 1) return lstm_scan_backward_tc(p, stream);
+  if (lstm_scan_cluster_supported(p.H) && lstm_scan_get_impl() == 1) return lstm_scan_backward_tc(p, stream);  // bias sums fused
+  int rc;
   switch (p.H) {
-    case 32: return bwd_dispatch<32>(p, stream);
-    case 64: return bwd_dispatch<64>(p, stream);
-    case 128: return bwd_dispatch<128>(p, stream);
-    case 256: return bwd_dispatch<256>(p, stream);
-    default: break;
+    case 32: rc = bwd_dispatch<32>(p, stream); break;
+    case 64: rc = bwd_dispatch<64>(p, stream); break;
+    case 128: rc = bwd_dispatch<128>(p, stream); break;
+    case 256: rc = bwd_dispatch<256>(p, stream); break;
+    default: rc = scan_backward_generic(p, stream); break;
   }
-  return scan_backward_generic(p, stream);
+  R2D2_TRY(rc);
+  if (p.dbias) {  // sum_t dgin_t == sum_s dgates_s
+    const float* src = p.repeat > 1 ? p.dgin : p.dgates;
+    R2D2_TRY(colsum(src, 4 * p.H, p.T * p.B, 4 * p.H, p.dbias, p.dbias2, stream));
+  }
+  return R2D2_OK;
 }
 
 }  // namespace r2d2

@@ -34,6 +34,8 @@ struct ScanBwdParams {
   float* dgin = nullptr;           // [T,B,4H] sum over the `repeat` steps sharing an input row (== dgates if repeat==1)
   int T = 0, B = 0, H = 0, repeat = 1;
   float* scratch = nullptr;        // generic path only: [2,B,H] (dh_rec, dc)
+  float* dbias = nullptr;          // optional [4H]: column sums of dgates over all steps and rows are ADDED here
+  float* dbias2 = nullptr;         // optional second copy (b_ih and b_hh receive the same gradient)
   int rows_per_cluster = 0;        // set by the tcgen05 dispatcher
 };
 

@@ -592,6 +592,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   const int ug = rank * 32 + lane;
   const size_t gstride = (size_t)4 * H;
   float dcn[NT], keep[NT][4];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};   // this thread's share of the bias gradient: sum of dG over its rows and all steps
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     dcn[j] = 0.f;
@@ -709,6 +710,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
         if (b < b_end) {
           float* go = p.dgates + ((size_t)s * B + b) * gstride + ug;
           go[0] = dgr[j][0]; go[H] = dgr[j][1]; go[2 * H] = dgr[j][2]; go[3 * H] = dgr[j][3];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bsum[q] += dgr[j][q];
           if (p.repeat > 1) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) keep[j][q] += dgr[j][q];
@@ -790,6 +793,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   }
   tc::fence_before_thread_sync();
   cluster.sync();
+  if (p.dbias) {   // CTA-level reduction over the 16 warps (same lane -> unit map), then one atomic per (gate, unit)
+    float* red = ps;       // [warp][4][32] = 8 KB over ps + pstage; all exchange traffic is complete after the cluster barrier
+#pragma unroll
+    for (int q = 0; q < 4; ++q) red[(w * 4 + q) * 32 + lane] = bsum[q];
+    __syncthreads();
+    if (tid < 128) {
+      const int q = tid >> 5;
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < TC_WARPS; ++ww) t += red[(ww * 4 + q) * 32 + lane];
+      atomicAdd(p.dbias + q * H + ug, t);
+      if (p.dbias2) atomicAdd(p.dbias2 + q * H + ug, t);
+    }
+  }
   if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, SM::TM_COLS); }
 }
 

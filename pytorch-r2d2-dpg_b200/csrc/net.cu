@@ -120,6 +120,7 @@ int net_backward(const NetShape& s, const NetParams& P, const NetParams* G, cons
     bp.dh_head = ws.dh_head; bp.head_first_step = first_row * repeat;
     bp.dgates = ws.gates; bp.dgin = dgin;
     bp.T = T; bp.B = B; bp.H = H; bp.repeat = repeat; bp.scratch = ws.scratch;
+    if (G) { bp.dbias = G->bih; bp.dbias2 = G->bhh; }   // db_ih = db_hh = sum of dG, accumulated inside the scan
     R2D2_TRY(lstm_scan_backward(bp, stream));
   }
   if (G) {
@@ -133,9 +134,9 @@ int net_backward(const NetShape& s, const NetParams& P, const NetParams* G, cons
       GemmParams g;
       g.A = dgin; g.lda = 4 * H; g.B = ws.z1; g.ldb = H; g.K = M;
       g.C = G->wih; g.ldc = H; g.M = 4 * H; g.N = H; g.split_k = gemm_suggest_split_k(4 * H, H, M);
+      g.reuse_packed_a = (repeat == 1);   // same dG operand as the dW_hh product just above
       R2D2_TRY(gemm_f32(g, GEMM_TN, stream));
     }
-    R2D2_TRY(colsum(dgin, 4 * H, M, 4 * H, G->bih, G->bhh, stream));
   }
   {  // d(pre-l1) = (dGin * W_ih) * (1 - z1^2), in place over z1
     GemmParams g;

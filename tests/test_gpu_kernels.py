@@ -47,12 +47,22 @@ GEMM_CASES = [
     (0, 130, 257, 77, 0, True, 1, 1),        # ragged everything
     (1, 257, 130, 77, 0, False, 0, 1),
     (2, 130, 257, 777, 0, False, 0, 3),
+    (0, 20480, 256, 17, 0, True, 1, 1),      # actor l1 at cfg-2 size (thin small-K kernel in default mode)
+    (0, 4099, 300, 3, 1, True, 1, 1),        # Pendulum critic l1: K = 3 + 1, N not a multiple of 256
+    (0, 20481, 6, 256, 0, True, 1, 1),       # actor head at cfg-2 size, odd row count
+    (1, 4097, 17, 512, 0, False, 2, 1),      # small-N NN with dtanh epilogue, N = 17
+    (0, 999, 1, 128, 0, True, 0, 1),         # Pendulum head, N = 1
+    (2, 6, 256, 20480, 0, False, 0, 74),     # dW3 at cfg-2 size
+    (2, 256, 17, 32000, 0, False, 0, 120),   # dW1 obs block at cfg-2 size
+    (2, 300, 6, 5000, 0, False, 0, 7),       # dW1 action block, wide side not a multiple of 256
 ]
 
 
-@pytest.fixture(params=["tc", "mma"])
+@pytest.fixture(params=["tc", "mma", "default"])
 def gemm_impl(request, nv):
-    nv.lib().r2d2_set_gemm_impl(2 if request.param == "tc" else 0)   # 2: tcgen05 path for every shape, incl. skinny
+    # 2: tcgen05 path for every shape; 0: mma.sync v1 kernel; 1 (default): tcgen05 + the fp32 streaming kernels of
+    # gemm_thin.cu for shapes with a dimension <= 32
+    nv.lib().r2d2_set_gemm_impl({"tc": 2, "mma": 0, "default": 1}[request.param])
     yield request.param
     nv.lib().r2d2_set_gemm_impl(1)
 
