@@ -272,7 +272,11 @@ int gemm_suggest_split_k(int M, int N, int K) {
 }
 
 int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
-  R2D2_REQUIRE(p.A && p.B && p.C, "null operand");
+  R2D2_REQUIRE((p.A || p.A_img) && p.B && p.C, "null operand");
+  if (p.A_img) {
+    R2D2_REQUIRE(p.K2 == 0, "packed A with a second K segment");
+    return gemm_f32_tc(p, layout, stream);
+  }
   R2D2_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "empty problem");
   R2D2_REQUIRE(p.split_k >= 1, "split_k");
   R2D2_REQUIRE(p.split_k == 1 || (p.epilogue == EPI_NONE && p.bias == nullptr), "split-K supports no epilogue");

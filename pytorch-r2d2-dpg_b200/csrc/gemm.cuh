@@ -32,6 +32,8 @@ struct GemmParams {
   const float* Z = nullptr;  long long ldz = 0;   // [M,N] aux for the epilogue
   int epilogue = EPI_NONE;
   int split_k = 1;           // >1: partial products are atomically added into C (C must be pre-zeroed)
+  const unsigned char* A_img = nullptr;   // tcgen05 path: A already in packed tile-major form (gemm_tc.cu image of this
+                             // call's layout and tiling, e.g. written by the BPTT scan); A / lda are ignored
   int reuse_packed_a = 0;    // tcgen05 path: A (pointer, shape, layout) is the operand the previous gemm_f32 call packed
                              // and its contents have not changed since -> skip the pack pass (dW_hh then dW_ih of a chain)
   int debug_flags = 0;       // dev only (env R2D2_GEMM_DEBUG): 1 = producers skip fetch+convert, 2 = skip MMAs, 4 = skip epilogue stores

@@ -277,21 +277,24 @@ int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   const int m_tiles = ceil_div(p.M, TBM), n_tiles = ceil_div(p.N, TBN);
   const int kt1 = ceil_div(p.K, TBK), kt2 = p.K2 > 0 ? ceil_div(p.K2, TBK) : 0;
   const int k_tiles = kt1 + kt2;
-  R2D2_TRY(ensure_scratch(g_pack_a, (size_t)m_tiles * k_tiles * TILE_BYTES));
+  if (!p.A_img) R2D2_TRY(ensure_scratch(g_pack_a, (size_t)m_tiles * k_tiles * TILE_BYTES));
   R2D2_TRY(ensure_scratch(g_pack_b, (size_t)n_tiles * k_tiles * TILE_BYTES));
   // key of the image currently held in g_pack_a: reuse is honoured only if the caller asks AND the key matches
   static struct { const float* ptr; long long ld; int mn, k, mn_major, k_tiles; cudaStream_t stream; } last_a = {};
   const bool reuse = p.reuse_packed_a && kt2 == 0 && last_a.ptr == p.A && last_a.ld == p.lda && last_a.mn == p.M &&
                      last_a.k == p.K && last_a.mn_major == (a_mn ? 1 : 0) && last_a.k_tiles == k_tiles && last_a.stream == stream;
-  if (!reuse) R2D2_TRY(launch_pack(p.A, p.lda, p.M, p.K, a_mn, m_tiles, k_tiles, 0, g_pack_a.ptr, stream));
-  last_a = {kt2 ? nullptr : p.A, p.lda, p.M, p.K, a_mn ? 1 : 0, k_tiles, stream};
+  if (!p.A_img) {
+    if (!reuse) R2D2_TRY(launch_pack(p.A, p.lda, p.M, p.K, a_mn, m_tiles, k_tiles, 0, g_pack_a.ptr, stream));
+    last_a = {kt2 ? nullptr : p.A, p.lda, p.M, p.K, a_mn ? 1 : 0, k_tiles, stream};
+  }
   R2D2_TRY(launch_pack(p.B, p.ldb, p.N, p.K, b_mn, n_tiles, k_tiles, 0, g_pack_b.ptr, stream));
   if (kt2) {
+    R2D2_REQUIRE(!p.A_img, "packed A with a second K segment");
     R2D2_TRY(launch_pack(p.A2, p.lda2, p.M, p.K2, a_mn, m_tiles, k_tiles, kt1, g_pack_a.ptr, stream));
     R2D2_TRY(launch_pack(p.B2, p.ldb2, p.N, p.K2, b_mn, n_tiles, k_tiles, kt1, g_pack_b.ptr, stream));
   }
   PackedGemmParams q;
-  q.pa = g_pack_a.ptr; q.pb = g_pack_b.ptr; q.k_tiles = k_tiles; q.C = p.C; q.ldc = p.ldc; q.M = p.M; q.N = p.N;
+  q.pa = p.A_img ? p.A_img : g_pack_a.ptr; q.pb = g_pack_b.ptr; q.k_tiles = k_tiles; q.C = p.C; q.ldc = p.ldc; q.M = p.M; q.N = p.N;
   q.bias = p.bias; q.Z = p.Z; q.ldz = p.ldz; q.epilogue = p.epilogue; q.split_k = p.split_k;
   q.a_mn = a_mn; q.b_mn = b_mn; q.debug_flags = p.debug_flags;
   dim3 grid(n_tiles, m_tiles, p.split_k);

@@ -21,26 +21,43 @@ __device__ __forceinline__ float apply_epilogue(float v, int epilogue, float z) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// small K.  Block = 256 threads = 32 rows x 256 columns per pass (thread: 8 rows x 4 columns), W resident in shared
-// memory for the whole (persistent) block, A rows staged per pass.
+// small K.  Block = 256 threads = 32 rows x 256 columns per pass (thread: 8 rows x 4 columns).  W stays in shared
+// memory for the whole (persistent) block; the A rows of the next pass arrive by cp.async while this pass computes.
 // ------------------------------------------------------------------------------------------------
-constexpr int SK_ROWS = 32, SK_COLS = 256, SK_KMAX = 32, SK_THREADS = 256;
+constexpr int SK_ROWS = 32, SK_COLS = 256, SK_KMAX = 32, SK_THREADS = 256, SK_WLD = SK_COLS + 4;
+
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <bool NN>
 __global__ void __launch_bounds__(SK_THREADS) thin_smallk_kernel(GemmParams p, int vec_c, int vec_z) {
-  __shared__ __align__(16) float Ws[SK_KMAX][SK_COLS];
-  __shared__ __align__(16) float As[SK_ROWS][SK_KMAX];
+  __shared__ __align__(16) float Ws[SK_KMAX][SK_WLD];        // row stride 260: transposed fill is 4-way, not 32-way, conflicted
+  __shared__ __align__(16) float As[2][SK_ROWS][SK_KMAX];
   const int tid = threadIdx.x;
   const int n0 = blockIdx.y * SK_COLS;
   const int Kt = p.K + p.K2;
-  for (int idx = tid; idx < SK_KMAX * SK_COLS; idx += SK_THREADS) {
-    const int k = idx / SK_COLS, n = n0 + idx % SK_COLS;
-    float v = 0.f;
-    if (n < p.N && k < Kt) {
-      if (NN) v = __ldg(p.B + (long long)k * p.ldb + n);
-      else    v = (k < p.K) ? __ldg(p.B + (long long)n * p.ldb + k) : __ldg(p.B2 + (long long)n * p.ldb2 + (k - p.K));
+  for (int idx = tid; idx < SK_KMAX * SK_WLD; idx += SK_THREADS) (&Ws[0][0])[idx] = 0.f;
+  for (int idx = tid; idx < 2 * SK_ROWS * SK_KMAX; idx += SK_THREADS) (&As[0][0][0])[idx] = 0.f;
+  __syncthreads();
+  {   // thread = column tid of the tile; the (<= 32) loads of a batch are all in flight before the first store
+    const int n = n0 + tid;
+    for (int kb = 0; kb < Kt; kb += 8) {
+      float wv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kb + i;
+        wv[i] = 0.f;
+        if (n < p.N && k < Kt) {
+          if (NN) wv[i] = __ldg(p.B + (long long)k * p.ldb + n);
+          else    wv[i] = (k < p.K) ? __ldg(p.B + (long long)n * p.ldb + k) : __ldg(p.B2 + (long long)n * p.ldb2 + (k - p.K));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (kb + i < SK_KMAX) Ws[kb + i][tid] = wv[i];
     }
-    Ws[k][idx % SK_COLS] = v;
   }
   const int cg = tid & 63, rgp = tid >> 6;
   const int col = n0 + cg * 4;
@@ -51,17 +68,26 @@ __global__ void __launch_bounds__(SK_THREADS) thin_smallk_kernel(GemmParams p, i
   }
   const int k4n = (Kt + 3) >> 2;
   const int row_tiles = (p.M + SK_ROWS - 1) / SK_ROWS;
-  for (int rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
-    const int r0 = rt * SK_ROWS;
-    __syncthreads();   // previous pass done with As (and, first time, Ws complete)
-    for (int idx = tid; idx < SK_ROWS * SK_KMAX; idx += SK_THREADS) {
-      const int r = idx / SK_KMAX, k = idx % SK_KMAX, row = r0 + r;
-      float v = 0.f;
-      if (row < p.M && k < Kt)
-        v = (k < p.K) ? __ldg(p.A + (long long)row * p.lda + k) : __ldg(p.A2 + (long long)row * p.lda2 + (k - p.K));
-      As[r][k] = v;
+  auto stage = [&](int rt, int buf) {   // rows past M keep the zeros of the initial fill or of an earlier tile: never stored
+    const int r = tid >> 3, row = rt * SK_ROWS + r;
+    if (row < p.M) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = (tid & 7) + 8 * j;
+        if (k < Kt) cp_async_4(&As[buf][r][k], (k < p.K) ? p.A + (long long)row * p.lda + k : p.A2 + (long long)row * p.lda2 + (k - p.K));
+      }
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+  int it = 0;
+  if ((int)blockIdx.x < row_tiles) stage(blockIdx.x, 0);
+  cp_async_wait_all();
+  __syncthreads();
+  const bool needs_z = p.epilogue == EPI_MUL_DTANH || p.epilogue == EPI_ADD_Z;
+  for (int rt = blockIdx.x; rt < row_tiles; rt += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int r0 = rt * SK_ROWS;
+    if (rt + (int)gridDim.x < row_tiles) stage(rt + gridDim.x, buf ^ 1);
     float acc[8][4];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -74,49 +100,54 @@ __global__ void __launch_bounds__(SK_THREADS) thin_smallk_kernel(GemmParams p, i
       const float4 w3 = *reinterpret_cast<const float4*>(&Ws[4 * k4 + 3][cg * 4]);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[rgp * 8 + r][4 * k4]);
-        acc[r][0] += a.x * w0.x + a.y * w1.x + a.z * w2.x + a.w * w3.x;
-        acc[r][1] += a.x * w0.y + a.y * w1.y + a.z * w2.y + a.w * w3.y;
-        acc[r][2] += a.x * w0.z + a.y * w1.z + a.z * w2.z + a.w * w3.z;
-        acc[r][3] += a.x * w0.w + a.y * w1.w + a.z * w2.w + a.w * w3.w;
+        const float4 a = *reinterpret_cast<const float4*>(&As[buf][rgp * 8 + r][4 * k4]);
+        acc[r][0] = fmaf(a.w, w3.x, fmaf(a.z, w2.x, fmaf(a.y, w1.x, fmaf(a.x, w0.x, acc[r][0]))));
+        acc[r][1] = fmaf(a.w, w3.y, fmaf(a.z, w2.y, fmaf(a.y, w1.y, fmaf(a.x, w0.y, acc[r][1]))));
+        acc[r][2] = fmaf(a.w, w3.z, fmaf(a.z, w2.z, fmaf(a.y, w1.z, fmaf(a.x, w0.z, acc[r][2]))));
+        acc[r][3] = fmaf(a.w, w3.w, fmaf(a.z, w2.w, fmaf(a.y, w1.w, fmaf(a.x, w0.w, acc[r][3]))));
       }
     }
-    if (col >= p.N) continue;
-    const bool full = col + 3 < p.N;
-    const bool needs_z = p.epilogue == EPI_MUL_DTANH || p.epilogue == EPI_ADD_Z;
+    if (col < p.N) {
+      const bool full = col + 3 < p.N;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int row = r0 + rgp * 8 + r;
-      if (row >= p.M) break;
-      float z[4] = {0.f, 0.f, 0.f, 0.f};
-      if (needs_z) {
-        const float* zp = p.Z + (long long)row * p.ldz + col;
-        if (full && vec_z) { const float4 t = *reinterpret_cast<const float4*>(zp); z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w; }
+      for (int r = 0; r < 8; ++r) {
+        const int row = r0 + rgp * 8 + r;
+        if (row >= p.M) break;
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (needs_z) {
+          const float* zp = p.Z + (long long)row * p.ldz + col;
+          if (full && vec_z) { const float4 t = *reinterpret_cast<const float4*>(zp); z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w; }
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (col + j < p.N) z[j] = zp[j];
+          }
+        }
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = apply_epilogue(acc[r][j], p.epilogue, z[j]);
+        float* cp = p.C + (long long)row * p.ldc + col;
+        if (full && vec_c) *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
         else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (col + j < p.N) z[j] = zp[j];
+          for (int j = 0; j < 4; ++j) if (col + j < p.N) cp[j] = v[j];
         }
       }
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = apply_epilogue(acc[r][j], p.epilogue, z[j]);
-      float* cp = p.C + (long long)row * p.ldc + col;
-      if (full && vec_c) *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-      else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (col + j < p.N) cp[j] = v[j];
-      }
     }
+    cp_async_wait_all();
+    __syncthreads();   // next tile landed; everyone is done reading this one
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// small N.  One warp per pair of rows; lane owns the k slices {128 j + 4 lane .. +3}; W^T[n][k] in shared memory.
+// small N.  One warp per group of R = 32 / NP rows; lane owns the k slices {128 j + 4 lane .. +3}; W^T[n][k] in shared
+// memory.  The R*NP = 32 partial sums of a lane are reduced across the warp with a halving exchange (31 shuffles):
+// afterwards lane L holds output (row L / NP, column L % NP).
 // ------------------------------------------------------------------------------------------------
 constexpr int SN_THREADS = 256;
 
 template <bool NN, int NP>
 __global__ void __launch_bounds__(SN_THREADS) thin_smalln_kernel(GemmParams p, int kpad) {
+  constexpr int R = 32 / NP;
   extern __shared__ __align__(16) float Wt[];   // [NP][kpad]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < NP * kpad; idx += SN_THREADS) {
@@ -128,60 +159,66 @@ __global__ void __launch_bounds__(SN_THREADS) thin_smalln_kernel(GemmParams p, i
   }
   __syncthreads();
   const int kchunks = kpad >> 7;
-  const int pairs = (p.M + 1) >> 1;
+  const int groups = (p.M + R - 1) / R;
   const bool needs_z = p.epilogue == EPI_MUL_DTANH || p.epilogue == EPI_ADD_Z;
-  for (int pr = blockIdx.x * (SN_THREADS / 32) + warp; pr < pairs; pr += gridDim.x * (SN_THREADS / 32)) {
-    const int row0 = 2 * pr, row1 = row0 + 1;
-    const bool has1 = row1 < p.M;
-    float acc0[NP], acc1[NP];
+  for (int g = blockIdx.x * (SN_THREADS / 32) + warp; g < groups; g += gridDim.x * (SN_THREADS / 32)) {
+    const int row0 = g * R;
+    float acc[32];
 #pragma unroll
-    for (int n = 0; n < NP; ++n) { acc0[n] = 0.f; acc1[n] = 0.f; }
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     for (int j = 0; j < kchunks; ++j) {
       const int k = j * 128 + lane * 4;
-      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-      if (k < p.K) {   // K % 4 == 0 is a dispatch precondition
-        a0 = __ldg(reinterpret_cast<const float4*>(p.A + (long long)row0 * p.lda + k));
-        if (has1) a1 = __ldg(reinterpret_cast<const float4*>(p.A + (long long)row1 * p.lda + k));
+      float4 a[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        a[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < p.K && row0 + r < p.M)   // K % 4 == 0 is a dispatch precondition
+          a[r] = __ldg(reinterpret_cast<const float4*>(p.A + (long long)(row0 + r) * p.lda + k));
       }
 #pragma unroll
       for (int n = 0; n < NP; ++n) {
         const float4 w = *reinterpret_cast<const float4*>(&Wt[n * kpad + k]);
-        acc0[n] += a0.x * w.x + a0.y * w.y + a0.z * w.z + a0.w * w.w;
-        acc1[n] += a1.x * w.x + a1.y * w.y + a1.z * w.z + a1.w * w.w;
-      }
-    }
-    float out0 = 0.f, out1 = 0.f;
 #pragma unroll
-    for (int n = 0; n < NP; ++n) {
-      const float s0 = warp_sum(acc0[n]), s1 = warp_sum(acc1[n]);
-      if (lane == n) { out0 = s0; out1 = s1; }
-    }
-    if (lane < p.N) {
-      const float b = p.bias ? __ldg(p.bias + lane) : 0.f;
-      const float z0 = needs_z ? p.Z[(long long)row0 * p.ldz + lane] : 0.f;
-      p.C[(long long)row0 * p.ldc + lane] = apply_epilogue(out0 + b, p.epilogue, z0);
-      if (has1) {
-        const float z1 = needs_z ? p.Z[(long long)row1 * p.ldz + lane] : 0.f;
-        p.C[(long long)row1 * p.ldc + lane] = apply_epilogue(out1 + b, p.epilogue, z1);
+        for (int r = 0; r < R; ++r) acc[r * NP + n] = fmaf(a[r].w, w.w, fmaf(a[r].z, w.z, fmaf(a[r].y, w.y, fmaf(a[r].x, w.x, acc[r * NP + n]))));
       }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = upper ? acc[i] : acc[i + off];
+        const float keep = upper ? acc[i + off] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    const int row = row0 + lane / NP, n = lane % NP;
+    if (row < p.M && n < p.N) {
+      const float b = p.bias ? __ldg(p.bias + n) : 0.f;
+      const float z = needs_z ? p.Z[(long long)row * p.ldz + n] : 0.f;
+      p.C[(long long)row * p.ldc + n] = apply_epilogue(acc[0] + b, p.epilogue, z);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // TN with one small output dimension: X[K rows][P] is the wide operand (thread = one of its columns), Y[K rows][Q<=32]
-// the narrow one (staged per 128-row chunk in shared memory, read as broadcast float4).  Accumulates into C with
-// atomics once per block (split-K contract of gemm_f32: C pre-zeroed by the caller).
+// the narrow one (staged per 32-row chunk in shared memory, read as broadcast float4).  X rows are fetched sixteen at a
+// time (the kernel is latency bound otherwise).  Accumulates into C with atomics once per block (split-K contract
+// of gemm_f32: C pre-zeroed by the caller); the block result goes through shared memory so that the atomics walk C
+// in address order whichever side is the narrow one.
 // ------------------------------------------------------------------------------------------------
-constexpr int TN_THREADS = 256, TN_CHUNK = 128;
+constexpr int TN_THREADS = 256, TN_CHUNK = 32, TN_BATCH = 16;
 
 template <int QP>
 __global__ void __launch_bounds__(TN_THREADS) thin_tn_kernel(const float* __restrict__ X, long long ldx, int P,
                                                              const float* __restrict__ Y, long long ldy, int Q, int K,
                                                              float* __restrict__ C, long long ldc, int small_is_m) {
   __shared__ __align__(16) float Ys[TN_CHUNK][QP];
+  __shared__ float Out[TN_THREADS][QP + 1];
   const int tid = threadIdx.x;
-  const int pc = blockIdx.y * TN_THREADS + tid;
+  const int p0 = blockIdx.y * TN_THREADS;
+  const int pc = p0 + tid;
   const bool pon = pc < P;
   float acc[QP];
 #pragma unroll
@@ -197,20 +234,35 @@ __global__ void __launch_bounds__(TN_THREADS) thin_tn_kernel(const float* __rest
     }
     __syncthreads();
     const float* xp = X + (long long)r0 * ldx + pc;
-#pragma unroll 4
-    for (int r = 0; r < nr; ++r) {
-      const float x = pon ? __ldg(xp + (long long)r * ldx) : 0.f;
+    for (int rb = 0; rb < nr; rb += TN_BATCH) {
+      float x[TN_BATCH];
 #pragma unroll
-      for (int q4 = 0; q4 < QP / 4; ++q4) {
-        const float4 y = *reinterpret_cast<const float4*>(&Ys[r][q4 * 4]);
-        acc[q4 * 4 + 0] += x * y.x; acc[q4 * 4 + 1] += x * y.y; acc[q4 * 4 + 2] += x * y.z; acc[q4 * 4 + 3] += x * y.w;
+      for (int i = 0; i < TN_BATCH; ++i) x[i] = (pon && rb + i < nr) ? __ldg(xp + (long long)(rb + i) * ldx) : 0.f;
+#pragma unroll
+      for (int i = 0; i < TN_BATCH; ++i) {
+#pragma unroll
+        for (int q4 = 0; q4 < QP / 4; ++q4) {
+          const float4 y = *reinterpret_cast<const float4*>(&Ys[rb + i][q4 * 4]);   // rows >= nr hold zeros
+          acc[q4 * 4 + 0] = fmaf(x[i], y.x, acc[q4 * 4 + 0]); acc[q4 * 4 + 1] = fmaf(x[i], y.y, acc[q4 * 4 + 1]);
+          acc[q4 * 4 + 2] = fmaf(x[i], y.z, acc[q4 * 4 + 2]); acc[q4 * 4 + 3] = fmaf(x[i], y.w, acc[q4 * 4 + 3]);
+        }
       }
     }
   }
-  if (!pon) return;
 #pragma unroll
-  for (int q = 0; q < QP; ++q) {
-    if (q < Q) atomicAdd(small_is_m ? C + (long long)q * ldc + pc : C + (long long)pc * ldc + q, acc[q]);
+  for (int q = 0; q < QP; ++q) Out[tid][q] = acc[q];
+  __syncthreads();
+  const int pn = min(TN_THREADS, P - p0);
+  if (small_is_m) {   // C[q][p]: p fastest
+    for (int idx = tid; idx < Q * pn; idx += TN_THREADS) {
+      const int q = idx / pn, pp = idx % pn;
+      atomicAdd(C + (long long)q * ldc + p0 + pp, Out[pp][q]);
+    }
+  } else {            // C[p][q]: q fastest
+    for (int idx = tid; idx < pn * Q; idx += TN_THREADS) {
+      const int pp = idx / Q, q = idx % Q;
+      atomicAdd(C + (long long)(p0 + pp) * ldc + q, Out[pp][q]);
+    }
   }
 }
 
@@ -222,8 +274,10 @@ template <int QP>
 int launch_thin_tn(const float* X, long long ldx, int P, const float* Y, long long ldy, int Q, int K, float* C,
                    long long ldc, int small_is_m, cudaStream_t stream) {
   const int chunks = ceil_div(K, TN_CHUNK), py = ceil_div(P, TN_THREADS);
-  int gx = chunks < 296 / py ? chunks : 296 / py;
+  int gx = 888 / py;                                   // ~6 resident blocks per SM
   if (gx < 1) gx = 1;
+  if (gx > chunks) gx = chunks;
+  gx = ceil_div(chunks, ceil_div(chunks, gx));         // equal number of chunks per block
   thin_tn_kernel<QP><<<dim3(gx, py), TN_THREADS, 0, stream>>>(X, ldx, P, Y, ldy, Q, K, C, ldc, small_is_m);
   count_launch();
   R2D2_CUDA_TRY(cudaGetLastError());
@@ -239,9 +293,9 @@ int launch_thin_smalln(const GemmParams& p, cudaStream_t stream) {
     R2D2_CUDA_TRY(cudaFuncSetAttribute(thin_smalln_kernel<NN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  const int pairs = (p.M + 1) / 2;
-  int grid = ceil_div(pairs, SN_THREADS / 32);
-  if (grid > 148 * 4) grid = 148 * 4;
+  const int groups = ceil_div(p.M, 32 / NP);
+  int grid = ceil_div(groups, SN_THREADS / 32);
+  if (grid > 148 * 6) grid = 148 * 6;
   thin_smalln_kernel<NN, NP><<<grid, SN_THREADS, smem, stream>>>(p, kpad);
   count_launch();
   R2D2_CUDA_TRY(cudaGetLastError());
@@ -279,8 +333,9 @@ int gemm_thin_try(const GemmParams& p, GemmLayout layout, cudaStream_t stream, b
   if (p.K + p.K2 <= SK_KMAX && (p.K2 == 0 || !nn)) {
     *handled = true;
     const int row_tiles = ceil_div(p.M, SK_ROWS), ny = ceil_div(p.N, SK_COLS);
-    int gx = row_tiles < 444 / ny ? row_tiles : 444 / ny;
+    int gx = 444 / ny;                                 // 3 resident blocks per SM (registers)
     if (gx < 1) gx = 1;
+    if (gx > row_tiles) gx = row_tiles;                // tiles go round-robin over the resident blocks: SM loads differ by <= 1 tile
     const int vec_c = aligned16(p.C, p.ldc) ? 1 : 0, vec_z = aligned16(p.Z, p.ldz) ? 1 : 0;
     if (nn) thin_smallk_kernel<true><<<dim3(gx, ny), SK_THREADS, 0, stream>>>(p, vec_c, vec_z);
     else    thin_smallk_kernel<false><<<dim3(gx, ny), SK_THREADS, 0, stream>>>(p, vec_c, vec_z);

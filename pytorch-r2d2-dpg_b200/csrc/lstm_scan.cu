@@ -528,6 +528,7 @@ int bwd_dispatch(const ScanBwdParams& p, cudaStream_t stream) {
 }  // namespace
 
 bool lstm_scan_cluster_supported(int H) { return H == 32 || H == 64 || H == 128 || H == 256; }
+bool lstm_scan_backward_emits_images(int H) { return lstm_scan_cluster_supported(H) && lstm_scan_get_impl() == 1; }
 
 static int g_scan_impl = -1;
 void lstm_scan_set_impl(int impl) { g_scan_impl = impl ? 1 : 0; }
@@ -574,6 +575,7 @@ int lstm_scan_backward(const ScanBwdParams& p, cudaStream_t stream) {
     case 256: rc = bwd_dispatch<256>(p, stream); break;
     default: rc = scan_backward_generic(p, stream); break;
   }
+  R2D2_REQUIRE(!p.skip_fp32, "skip_fp32 needs the tcgen05 scan (lstm_scan_backward_emits_images)");
   R2D2_TRY(rc);
   if (p.dbias) {  // sum_t dgin_t == sum_s dgates_s
     const float* src = p.repeat > 1 ? p.dgin : p.dgates;

@@ -36,8 +36,18 @@ struct ScanBwdParams {
   float* scratch = nullptr;        // generic path only: [2,B,H] (dh_rec, dc)
   float* dbias = nullptr;          // optional [4H]: column sums of dgates over all steps and rows are ADDED here
   float* dbias2 = nullptr;         // optional second copy (b_ih and b_hh receive the same gradient)
+  // tcgen05 path only: the scan can write dG directly as the packed bf16 hi/lo operand images of the three GEMMs that
+  // consume it (tile formats of gemm_tc.cu), so that no pack pass and no fp32 round trip is needed:
+  unsigned char* img_k = nullptr;       // dgin   as A of dgin * W_ih  : K-major tiles  [ceil(T*B/128)][4H/32][16 KB]
+  unsigned char* img_mn_dg = nullptr;   // dgates as A of dgates^T * h : MN-major tiles [4H/128][ceil(S*B/32)][16 KB]
+  unsigned char* img_mn_gin = nullptr;  // dgin   as A of dgin^T * z1  : MN-major tiles [4H/128][ceil(T*B/32)][16 KB]
+                                        // (pass img_mn_dg again when repeat == 1: the two tensors coincide)
+  int skip_fp32 = 0;                    // 1: do not store fp32 dgates / dgin (every consumer reads the images)
   int rows_per_cluster = 0;        // set by the tcgen05 dispatcher
 };
+
+// true when lstm_scan_backward will honour img_* (persistent tcgen05 kernels selected for this hidden size)
+bool lstm_scan_backward_emits_images(int H);
 
 // true when the persistent cluster kernels cover this hidden size (H in {32,64,128,256})
 bool lstm_scan_cluster_supported(int H);

@@ -554,7 +554,8 @@ struct TcBwdSmem {
   static constexpr int OFF_PS = OFF_DG + 2 * DG_PLANE;            // [buf][src][n][32]
   static constexpr int OFF_PSTAGE = OFF_PS + 2 * C * PS_SLOT;     // [dbuf][owner][n][32]
   static constexpr int OFF_BAR = OFF_PSTAGE + 2 * C * PS_SLOT;
-  static constexpr int BYTES = OFF_BAR + 64;
+  static constexpr int OFF_GSTAGE = OFF_BAR + 64;                 // [plane][k-chunk][n][8 bf16]: per-row dgin sums (repeat > 1)
+  static constexpr int BYTES = OFF_GSTAGE + 2 * DG_PLANE;
   static_assert(BYTES <= 232448, "backward scan tile does not fit in 227 KB of shared memory");
 };
 
@@ -580,6 +581,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   uint64_t* mma_done = ps_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
   volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  unsigned char* gst = smem + SM::OFF_GSTAGE;
+  const int kt_k = 4 * H / 32;                                    // k tiles of the K-major image (gate columns / 32)
+  const int kt_mn_dg = (S * B + 31) / 32, kt_mn_gin = (p.T * B + 31) / 32;
 
   if (tid == 0) {
     tc::mbar_init(&ps_full[0], 1);
@@ -670,6 +674,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       if (!tc::mbar_wait(&ps_full[buf], ((it - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 3); }
     }
 
+    const bool emit_gin = p.repeat > 1 && (s % p.repeat == 0);
     // ---- pointwise backward of the cell (thread = (unit = lane, row r8 of row group e)); the dG values go to the MMA
     // operand tile first - their HBM copies are written below, after the tensor-core step has been started
     float dgr[NT][4];
@@ -700,35 +705,83 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
           const int off = ((q * 4 + (lane >> 3)) * NB + n) * 16 + (lane & 7) * 2;
           *reinterpret_cast<__nv_bfloat16*>(dgs + off) = hi;
           *reinterpret_cast<__nv_bfloat16*>(dgs + SM::DG_PLANE + off) = lo;
+          bsum[q] += dgr[j][q];
+        }
+        if (p.repeat > 1) {   // dgin row = sum of dG over the steps that share the input row
+#pragma unroll
+          for (int q = 0; q < 4; ++q) keep[j][q] += dgr[j][q];
+          if (emit_gin) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (!p.skip_fp32) p.dgin[((size_t)t * B + b) * gstride + q * H + ug] = keep[j][q];
+              __nv_bfloat16 hi, lo;
+              split_bf16(keep[j][q], hi, lo);
+              const int off = ((q * 4 + (lane >> 3)) * NB + n) * 16 + (lane & 7) * 2;
+              *reinterpret_cast<__nv_bfloat16*>(gst + off) = hi;
+              *reinterpret_cast<__nv_bfloat16*>(gst + SM::DG_PLANE + off) = lo;
+              keep[j][q] = 0.f;
+            }
+          }
         }
       }
     }
     auto store_dg = [&]() {
+      if (!p.skip_fp32) {
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const int b = b0 + 8 * (half + 2 * j) + r8;
-        if (b < b_end) {
-          float* go = p.dgates + ((size_t)s * B + b) * gstride + ug;
-          go[0] = dgr[j][0]; go[H] = dgr[j][1]; go[2 * H] = dgr[j][2]; go[3 * H] = dgr[j][3];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) bsum[q] += dgr[j][q];
-          if (p.repeat > 1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) keep[j][q] += dgr[j][q];
-            if (s % p.repeat == 0) {
-              float* gi = p.dgin + ((size_t)t * B + b) * gstride + ug;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { gi[q * H] = keep[j][q]; keep[j][q] = 0.f; }
+        for (int j = 0; j < NT; ++j) {
+          const int b = b0 + 8 * (half + 2 * j) + r8;
+          if (b < b_end) {
+            float* go = p.dgates + ((size_t)s * B + b) * gstride + ug;
+            go[0] = dgr[j][0]; go[H] = dgr[j][1]; go[2 * H] = dgr[j][2]; go[3 * H] = dgr[j][3];
+          }
+        }
+      }
+      // ---- packed operand images straight from the MMA operand tile in shared memory.  Eight lanes = the eight rows
+      // of one core matrix (128 contiguous bytes in either image), four core matrices per warp instruction.
+      if (p.img_k || p.img_mn_dg || p.img_mn_gin) {
+        for (int idx = w * 4 + (lane >> 3); idx < RG * 16; idx += TC_WARPS * 4) {
+          const int kc = idx & 15, n = (idx >> 4) * 8 + (lane & 7);
+          if (n >= n_valid) continue;
+          const int c8 = (kc >> 2) * (H / 8) + rank * 4 + (kc & 3);          // global gate column / 8
+          const uint4 hi = *reinterpret_cast<const uint4*>(dgs + (kc * NB + n) * 16);
+          const uint4 lo = *reinterpret_cast<const uint4*>(dgs + SM::DG_PLANE + (kc * NB + n) * 16);
+          const size_t m = (size_t)s * B + b0 + n;
+          if (p.img_mn_dg) {
+            unsigned char* d = p.img_mn_dg + ((size_t)(c8 >> 4) * kt_mn_dg + (m >> 5)) * 16384 +
+                               ((((m & 31) >> 3) * 128) + (c8 & 15) * 8 + (m & 7)) * 16;
+            *reinterpret_cast<uint4*>(d) = hi;
+            *reinterpret_cast<uint4*>(d + 8192) = lo;
+          }
+          if (p.img_k && p.repeat == 1) {
+            unsigned char* d = p.img_k + ((size_t)(m >> 7) * kt_k + (c8 >> 2)) * 16384 +
+                               ((((m & 127) >> 3) * 32) + (c8 & 3) * 8 + (m & 7)) * 16;
+            *reinterpret_cast<uint4*>(d) = hi;
+            *reinterpret_cast<uint4*>(d + 8192) = lo;
+          }
+          if (emit_gin) {
+            const uint4 ghi = *reinterpret_cast<const uint4*>(gst + (kc * NB + n) * 16);
+            const uint4 glo = *reinterpret_cast<const uint4*>(gst + SM::DG_PLANE + (kc * NB + n) * 16);
+            const size_t mg = (size_t)t * B + b0 + n;
+            if (p.img_mn_gin) {
+              unsigned char* d = p.img_mn_gin + ((size_t)(c8 >> 4) * kt_mn_gin + (mg >> 5)) * 16384 +
+                                 ((((mg & 31) >> 3) * 128) + (c8 & 15) * 8 + (mg & 7)) * 16;
+              *reinterpret_cast<uint4*>(d) = ghi;
+              *reinterpret_cast<uint4*>(d + 8192) = glo;
+            }
+            if (p.img_k) {
+              unsigned char* d = p.img_k + ((size_t)(mg >> 7) * kt_k + (c8 >> 2)) * 16384 +
+                                 ((((mg & 127) >> 3) * 32) + (c8 & 3) * 8 + (mg & 7)) * 16;
+              *reinterpret_cast<uint4*>(d) = ghi;
+              *reinterpret_cast<uint4*>(d + 8192) = glo;
             }
           }
         }
       }
     };
-    if (s == 0) store_dg();
-    if (s == 0) break;  // dh_{-1} is not needed: the initial state is data, not a parameter
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
     __syncthreads();
+    if (s == 0) { store_dg(); break; }  // dh_{-1} is not needed: the initial state is data, not a parameter
 
     if (w_u == 0) {
       tc::fence_after_thread_sync();
@@ -893,6 +946,21 @@ int fwd_tc(const ScanFwdParams& p_in, cudaStream_t stream) {
 template <int H>
 int bwd_tc(const ScanBwdParams& p_in, cudaStream_t stream) {
   ScanBwdParams p = p_in;
+  R2D2_REQUIRE(!p.skip_fp32 || (p.img_k && (p.repeat == 1 || p.img_mn_gin || !p.img_mn_dg)), "skip_fp32 without operand images");
+  {  // rows of the last tile that no batch row maps to must read as zeros in the GEMMs
+    const size_t rows_g = (size_t)p.T * p.B, rows_d = (size_t)p.T * p.repeat * p.B;
+    const size_t mn_tiles = 4 * H / 128 > 0 ? 4 * H / 128 : 1;
+    if (p.img_k && rows_g % 128 != 0)
+      R2D2_CUDA_TRY(cudaMemsetAsync(p.img_k + (rows_g / 128) * (size_t)(4 * H / 32) * 16384, 0, (size_t)(4 * H / 32) * 16384, stream));
+    if (p.img_mn_dg && rows_d % 32 != 0) {
+      const size_t kt = (rows_d + 31) / 32;
+      R2D2_CUDA_TRY(cudaMemset2DAsync(p.img_mn_dg + (kt - 1) * 16384, kt * 16384, 0, 16384, mn_tiles, stream));
+    }
+    if (p.img_mn_gin && p.img_mn_gin != p.img_mn_dg && rows_g % 32 != 0) {
+      const size_t kt = (rows_g + 31) / 32;
+      R2D2_CUDA_TRY(cudaMemset2DAsync(p.img_mn_gin + (kt - 1) * 16384, kt * 16384, 0, 16384, mn_tiles, stream));
+    }
+  }
   const Tiling t = pick_tiling<H>(p.B, lstm_scan_bwd_tc_kernel<H, 16>, TcBwdSmem<H, 16>::BYTES,
                                   lstm_scan_bwd_tc_kernel<H, 32>, TcBwdSmem<H, 32>::BYTES);
   p.rows_per_cluster = t.rows_per_cluster;

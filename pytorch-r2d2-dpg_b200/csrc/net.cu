@@ -7,6 +7,7 @@
 namespace r2d2 {
 
 static size_t align64(size_t n) { return (n + 63) & ~(size_t)63; }  // 256-byte aligned sub-buffers
+static size_t pad_to(size_t n, size_t m) { return (n + m - 1) / m * m; }
 
 size_t ChainWs::floats(const NetShape& s, int T, int B, int repeat) {
   const size_t H = s.hidden, A = s.act, S = (size_t)T * repeat, TB = (size_t)T * B;
@@ -23,6 +24,11 @@ size_t ChainWs::floats(const NetShape& s, int T, int B, int repeat) {
   const size_t sb = lstm_scan_bwd_scratch_floats(B, s.hidden);
   if (sb > sc) sc = sb;
   n += align64(sc + 64);
+  if (lstm_scan_cluster_supported(s.hidden)) {   // operand images, 4 bytes per element like the fp32 tensors they replace
+    n += align64(pad_to(TB, 128) * 4 * H);
+    n += align64(pad_to(S * B, 32) * 4 * H);
+    if (repeat > 1) n += align64(pad_to(TB, 32) * 4 * H);
+  }
   return n;
 }
 
@@ -45,6 +51,11 @@ ChainWs ChainWs::carve(float* base, const NetShape& s, int T, int B, int repeat)
   const size_t sb = lstm_scan_bwd_scratch_floats(B, s.hidden);
   if (sb > sc) sc = sb;
   w.scratch = take(sc + 64);
+  if (lstm_scan_cluster_supported(s.hidden)) {
+    w.img_k = reinterpret_cast<unsigned char*>(take(pad_to(TB, 128) * 4 * H));
+    w.img_mn_dg = reinterpret_cast<unsigned char*>(take(pad_to(S * B, 32) * 4 * H));
+    w.img_mn_gin = (repeat > 1) ? reinterpret_cast<unsigned char*>(take(pad_to(TB, 32) * 4 * H)) : w.img_mn_dg;
+  }
   return w;
 }
 
@@ -114,6 +125,7 @@ int net_backward(const NetShape& s, const NetParams& P, const NetParams* G, cons
     R2D2_TRY(gemm_f32(g, GEMM_NN, stream));
   }
   float* dgin = (repeat > 1) ? ws.gin : ws.gates;
+  const bool use_img = ws.img_k != nullptr && lstm_scan_backward_emits_images(H) && gemm_get_impl() != 0;
   {
     ScanBwdParams bp;
     bp.gates = ws.gates; bp.hs = ws.hs; bp.cs = ws.cs; bp.whh = P.whh;
@@ -121,18 +133,25 @@ int net_backward(const NetShape& s, const NetParams& P, const NetParams* G, cons
     bp.dgates = ws.gates; bp.dgin = dgin;
     bp.T = T; bp.B = B; bp.H = H; bp.repeat = repeat; bp.scratch = ws.scratch;
     if (G) { bp.dbias = G->bih; bp.dbias2 = G->bhh; }   // db_ih = db_hh = sum of dG, accumulated inside the scan
+    if (use_img) {   // dG leaves the scan as the packed operands of the three GEMMs below: no pack pass, no fp32 copy
+      bp.img_k = ws.img_k;
+      if (G) { bp.img_mn_dg = ws.img_mn_dg; bp.img_mn_gin = ws.img_mn_gin; }
+      bp.skip_fp32 = 1;
+    }
     R2D2_TRY(lstm_scan_backward(bp, stream));
   }
   if (G) {
     {  // dW_hh = sum_s dG_s^T h_{s-1}
       GemmParams g;
       g.A = ws.gates; g.lda = 4 * H; g.B = ws.hs; g.ldb = H; g.K = S * B;
+      if (use_img) g.A_img = ws.img_mn_dg;
       g.C = G->whh; g.ldc = H; g.M = 4 * H; g.N = H; g.split_k = gemm_suggest_split_k(4 * H, H, S * B);
       R2D2_TRY(gemm_f32(g, GEMM_TN, stream));
     }
     {  // dW_ih = sum_t dGin_t^T z1_t
       GemmParams g;
       g.A = dgin; g.lda = 4 * H; g.B = ws.z1; g.ldb = H; g.K = M;
+      if (use_img) g.A_img = ws.img_mn_gin;
       g.C = G->wih; g.ldc = H; g.M = 4 * H; g.N = H; g.split_k = gemm_suggest_split_k(4 * H, H, M);
       g.reuse_packed_a = (repeat == 1);   // same dG operand as the dW_hh product just above
       R2D2_TRY(gemm_f32(g, GEMM_TN, stream));
@@ -141,6 +160,7 @@ int net_backward(const NetShape& s, const NetParams& P, const NetParams* G, cons
   {  // d(pre-l1) = (dGin * W_ih) * (1 - z1^2), in place over z1
     GemmParams g;
     g.A = dgin; g.lda = 4 * H; g.B = P.wih; g.ldb = H; g.K = 4 * H;
+    if (use_img) g.A_img = ws.img_k;
     g.C = ws.z1; g.ldc = H; g.M = M; g.N = H; g.Z = ws.z1; g.ldz = H; g.epilogue = EPI_MUL_DTANH;
     R2D2_TRY(gemm_f32(g, GEMM_NN, stream));
   }
