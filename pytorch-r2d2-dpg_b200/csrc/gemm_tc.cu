@@ -20,13 +20,19 @@
 namespace r2d2 {
 namespace {
 
-constexpr int TBM = 128, TBN = 128, TBK = 32, TSTAGES = 3;
+constexpr int TBM = 128, TBN = 128, TBK = 32;
 constexpr int PLANE_BYTES = 128 * TBK * 2;     // 8 KB: one bf16 plane of a 128 x 32 operand tile
 constexpr int TILE_BYTES = 2 * PLANE_BYTES;    // 16 KB: hi plane + lo plane of one operand tile
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;    // A tile + B tile
-constexpr int OFF_BARS = TSTAGES * STAGE_BYTES;
-constexpr int PACKED_GEMM_SMEM = OFF_BARS + 128;
 constexpr int PACKED_GEMM_THREADS = 320;       // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+// NBT = B tiles (of 128 columns) per CTA.  NBT = 2 halves the number of times the A images are pulled from L2 (the
+// kernel is bound by the L2 -> shared-memory path, profiles/r01_summary.md); both shapes keep ~96 KB of stages and
+// at most 256 TMEM columns per CTA so that two CTAs share an SM and overlap each other's epilogue.
+template <int NBT> struct PackedCfg {
+  static constexpr int STAGES = NBT == 1 ? 3 : 2;
+  static constexpr int STAGE_BYTES = (1 + NBT) * TILE_BYTES;
+  static constexpr int OFF_BARS = STAGES * STAGE_BYTES;
+  static constexpr int SMEM = OFF_BARS + 128;
+};
 
 // ---- operand tile image (shared with the MMA descriptors below) --------------------------------------------------
 // a tile is 512 groups of 8 elements; group `id` lives at byte id*16 of each plane.
@@ -86,55 +92,67 @@ struct PackedGemmParams {
   int debug_flags;
 };
 
+template <int NBT>
 __global__ void __launch_bounds__(PACKED_GEMM_THREADS, 2) gemm_packed_kernel(PackedGemmParams p) {
+  using CFG = PackedCfg<NBT>;
+  constexpr int TSTAGES = CFG::STAGES, STAGE_BYTES = CFG::STAGE_BYTES;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BARS);   // [TSTAGES] bytes landed
-  uint64_t* empty = full + TSTAGES;                                // [TSTAGES] MMAs retired
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + CFG::OFF_BARS);   // [TSTAGES] bytes landed
+  uint64_t* empty = full + TSTAGES;                                     // [TSTAGES] MMAs retired
   uint64_t* accum_full = empty + TSTAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int m_tile = blockIdx.y, n_tile = blockIdx.x;
-  const int m0 = m_tile * TBM, n0 = n_tile * TBN;
+  const int m_tile = blockIdx.y, n_blk = blockIdx.x;
+  const int m0 = m_tile * TBM, n0 = n_blk * TBN * NBT;
   const int per_split = (p.k_tiles + p.split_k - 1) / p.split_k;
   const int t_begin = blockIdx.z * per_split;
   const int t_end = min(p.k_tiles, t_begin + per_split);
   if (t_begin >= t_end) return;
   const int n_tiles = t_end - t_begin;
-  int n_eff = min(TBN, p.N - n0);
-  n_eff = (n_eff + 15) & ~15;
+  int n_eff[NBT], nb_live = 0;                       // columns of each B tile (rounded up to the MMA granule), live tiles
+#pragma unroll
+  for (int j = 0; j < NBT; ++j) {
+    int e = min(TBN, p.N - n0 - j * TBN);
+    n_eff[j] = e > 0 ? ((e + 15) & ~15) : 0;
+    if (e > 0) nb_live = j + 1;
+  }
 
   if (tid == 0) {
     for (int s = 0; s < TSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(accum_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (w_u == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, TBN); }
+  if (w_u == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, TBN * NBT); }
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (w_u == 0) {
-    // ================= producer: two 16 KB bulk copies per k tile =================
+    // ================= producer: one 16 KB bulk copy per operand tile and k tile =================
     if (tc::elect_one()) {
       const unsigned char* a_src = p.pa + ((size_t)m_tile * p.k_tiles + t_begin) * TILE_BYTES;
-      const unsigned char* b_src = p.pb + ((size_t)n_tile * p.k_tiles + t_begin) * TILE_BYTES;
+      const unsigned char* b_src = p.pb + ((size_t)(n_blk * NBT) * p.k_tiles + t_begin) * TILE_BYTES;
       const uint32_t smem_base = tc::smem_u32(smem);
       for (int i = 0; i < n_tiles; ++i) {
         const int s = i % TSTAGES;
         mbar_wait_spin(&empty[s], ((i / TSTAGES) & 1) ^ 1);
         const uint32_t bar = tc::smem_u32(&full[s]);
-        tc::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)((1 + nb_live) * TILE_BYTES));
         tc::bulk_copy_g2s(smem_base + s * STAGE_BYTES, a_src + (size_t)i * TILE_BYTES, TILE_BYTES, bar);
-        tc::bulk_copy_g2s(smem_base + s * STAGE_BYTES + TILE_BYTES, b_src + (size_t)i * TILE_BYTES, TILE_BYTES, bar);
+#pragma unroll
+        for (int j = 0; j < NBT; ++j)
+          if (j < nb_live)
+            tc::bulk_copy_g2s(smem_base + s * STAGE_BYTES + (1 + j) * TILE_BYTES,
+                              b_src + ((size_t)j * p.k_tiles + i) * TILE_BYTES, TILE_BYTES, bar);
       }
     }
     __syncwarp();
   } else if (w_u == 1) {
     // ================= MMA issuer =================
-    const uint32_t idesc = tc::make_idesc_bf16_f32(TBM, n_eff) | ((p.a_mn ? 1u : 0u) << 15) | ((p.b_mn ? 1u : 0u) << 16);
+    const uint32_t idesc_base = ((p.a_mn ? 1u : 0u) << 15) | ((p.b_mn ? 1u : 0u) << 16);
     const uint64_t da0 = p.a_mn ? tc::make_smem_desc(tc::smem_u32(smem), 2048, 128) : tc::make_smem_desc(tc::smem_u32(smem), 128, 512);
     const uint64_t db0 = p.b_mn ? tc::make_smem_desc(tc::smem_u32(smem), 2048, 128) : tc::make_smem_desc(tc::smem_u32(smem), 128, 512);
     const int a_ks = p.a_mn ? 4096 : 256, b_ks = p.b_mn ? 4096 : 256;   // byte advance per K=16 step
@@ -145,17 +163,23 @@ __global__ void __launch_bounds__(PACKED_GEMM_THREADS, 2) gemm_packed_kernel(Pac
       tc::fence_after_thread_sync();
       if (tc::elect_one()) {
         const uint64_t dsa = da0 + (uint64_t)((s * STAGE_BYTES) >> 4);
-        const uint64_t dsb = db0 + (uint64_t)((s * STAGE_BYTES + TILE_BYTES) >> 4);
 #pragma unroll
-        for (int ks = 0; ks < TBK / 16; ++ks) {
-          const uint64_t a_hi = dsa + (uint64_t)((ks * a_ks) >> 4);
-          const uint64_t a_lo = a_hi + (uint64_t)(PLANE_BYTES >> 4);
-          const uint64_t b_hi = dsb + (uint64_t)((ks * b_ks) >> 4);
-          const uint64_t b_lo = b_hi + (uint64_t)(PLANE_BYTES >> 4);
-          if (p.debug_flags & 2) continue;
-          tc::mma_bf16_ss(tmem_base, a_lo, b_hi, idesc, (i | ks) != 0);
-          tc::mma_bf16_ss(tmem_base, a_hi, b_lo, idesc, true);
-          tc::mma_bf16_ss(tmem_base, a_hi, b_hi, idesc, true);
+        for (int j = 0; j < NBT; ++j) {
+          if (j >= nb_live) continue;
+          const uint32_t idesc = tc::make_idesc_bf16_f32(TBM, n_eff[j]) | idesc_base;
+          const uint64_t dsb = db0 + (uint64_t)((s * STAGE_BYTES + (1 + j) * TILE_BYTES) >> 4);
+          const uint32_t d = tmem_base + j * TBN;
+#pragma unroll
+          for (int ks = 0; ks < TBK / 16; ++ks) {
+            const uint64_t a_hi = dsa + (uint64_t)((ks * a_ks) >> 4);
+            const uint64_t a_lo = a_hi + (uint64_t)(PLANE_BYTES >> 4);
+            const uint64_t b_hi = dsb + (uint64_t)((ks * b_ks) >> 4);
+            const uint64_t b_lo = b_hi + (uint64_t)(PLANE_BYTES >> 4);
+            if (p.debug_flags & 2) continue;
+            tc::mma_bf16_ss(d, a_lo, b_hi, idesc, (i | ks) != 0);
+            tc::mma_bf16_ss(d, a_hi, b_lo, idesc, true);
+            tc::mma_bf16_ss(d, a_hi, b_hi, idesc, true);
+          }
         }
         tc::mma_commit(&empty[s]);
         if (i + 1 == n_tiles) tc::mma_commit(accum_full);
@@ -164,69 +188,86 @@ __global__ void __launch_bounds__(PACKED_GEMM_THREADS, 2) gemm_packed_kernel(Pac
     }
   } else {
     // ================= epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ==========
+    // tcgen05.ld hands every lane one ROW of the tile; stored like that, each lane would write its own 32-byte piece
+    // of a different cache line (measured: the x*W_ih^T product was bound by those partial-line writes).  So every
+    // warp transposes 32 x 32 blocks through a private 4.5 KB slot of the (now idle) stage buffers and does bias /
+    // activation / Z reads / stores with lane = column: 128 contiguous bytes per row, 4 rows per instruction.
     mbar_wait_spin(accum_full, 0);
     __syncwarp();
     tc::fence_after_thread_sync();
     const int q = w_u & 3, half = (w_u - 2) >> 2;
-    const int row = m0 + q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool vec_c = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
     const bool vec_z = p.Z && ((reinterpret_cast<uintptr_t>(p.Z) & 15) == 0) && (p.ldz % 4 == 0);
     const bool vec_b = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
-    const int c_begin = half * (TBN / 2), c_end = min(n_eff, c_begin + TBN / 2);
-    for (int c0 = c_begin; c0 < c_end; c0 += 8) {
-      float v[8];
-      __syncwarp();                                          // tcgen05.ld is warp-collective: reconverge first
-      tc::tmem_ld_32x32b_x8(lane_base + (uint32_t)c0, v);
-      const int col = n0 + c0;
-      if (row >= p.M || col >= p.N || (p.debug_flags & 4)) continue;
-      const int nv = min(8, p.N - col);
-      if (p.bias) {
-        if (vec_b && nv == 8) {                               // same address for the whole warp: one broadcast load
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        } else {
+    const int n_tot = (nb_live - 1) * TBN + n_eff[nb_live - 1];     // accumulator columns in use
+    constexpr int HALF_COLS = TBN * NBT / 2, SLD = 36;
+    const int c_begin = half * HALF_COLS, c_end = min(n_tot, c_begin + HALF_COLS);
+    float* stg = reinterpret_cast<float*>(smem) + (w_u - 2) * 32 * SLD;
+    const int cc = lane & 7, rr = lane >> 3;
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) if (j < nv) v[j] += __ldg(p.bias + col + j);
+      for (int k = 0; k < 4; ++k) {
+        if (c0 + 8 * k < c_end) {                                // warp-uniform; c_end is a multiple of 16
+          float v[8];
+          tc::tmem_ld_32x32b_x8(lane_base + (uint32_t)(c0 + 8 * k), v);
+          *reinterpret_cast<float4*>(&stg[lane * SLD + 8 * k]) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(&stg[lane * SLD + 8 * k + 4]) = make_float4(v[4], v[5], v[6], v[7]);
         }
       }
-      if (p.epilogue == EPI_TANH) {
+      __syncwarp();
+      const int col = n0 + c0 + cc * 4;
+      const int nv = min(4, p.N - col);                          // <= 0: nothing to write for this lane
+      const bool live = (c0 + cc * 4 < c_end) && nv > 0 && !(p.debug_flags & 4);
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live && p.bias) {
+        if (vec_b && nv == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col)); bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w; }
+        else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
-      } else if (p.epilogue == EPI_MUL_DTANH || p.epilogue == EPI_ADD_Z) {
-        const float* z = p.Z + (long long)row * p.ldz + col;
-        float zz[8];
-        if (vec_z && nv == 8) {
-          const float4 z0 = *reinterpret_cast<const float4*>(z), z1 = *reinterpret_cast<const float4*>(z + 4);
-          zz[0] = z0.x; zz[1] = z0.y; zz[2] = z0.z; zz[3] = z0.w; zz[4] = z1.x; zz[5] = z1.y; zz[6] = z1.z; zz[7] = z1.w;
+          for (int j = 0; j < 4; ++j) if (j < nv) bv[j] = __ldg(p.bias + col + j);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rr, row = m0 + q * 32 + r;
+        if (!live || row >= p.M) continue;
+        const float4 a = *reinterpret_cast<const float4*>(&stg[r * SLD + cc * 4]);
+        float v[4] = {a.x + bv[0], a.y + bv[1], a.z + bv[2], a.w + bv[3]};
+        if (p.epilogue == EPI_TANH) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = tanhf(v[j]);
+        } else if (p.epilogue == EPI_MUL_DTANH || p.epilogue == EPI_ADD_Z) {
+          const float* z = p.Z + (long long)row * p.ldz + col;
+          float zz[4] = {0.f, 0.f, 0.f, 0.f};
+          if (vec_z && nv == 4) { const float4 t = *reinterpret_cast<const float4*>(z); zz[0] = t.x; zz[1] = t.y; zz[2] = t.z; zz[3] = t.w; }
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nv) zz[j] = z[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = (p.epilogue == EPI_MUL_DTANH) ? v[j] * (1.f - zz[j] * zz[j]) : v[j] + zz[j];
+        }
+        float* cp = p.C + (long long)row * p.ldc + col;
+        if (p.split_k > 1) {
+          if (vec_c && nv == 4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(cp + j, v[j]);
+          }
+        } else if (vec_c && nv == 4) {
+          *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) zz[j] = (j < nv) ? z[j] : 0.f;
+          for (int j = 0; j < 4; ++j) if (j < nv) cp[j] = v[j];
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (p.epilogue == EPI_MUL_DTANH) ? v[j] * (1.f - zz[j] * zz[j]) : v[j] + zz[j];
       }
-      float* cp = p.C + (long long)row * p.ldc + col;
-      if (p.split_k > 1) {
-        if (vec_c && nv == 8) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-          asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) if (j < nv) atomicAdd(cp + j, v[j]);
-        }
-      } else if (vec_c && nv == 8) {
-        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (j < nv) cp[j] = v[j];
-      }
+      __syncwarp();
     }
     tc::fence_before_thread_sync();
   }
   __syncthreads();
-  if (w_u == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, TBN); }
+  if (w_u == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, TBN * NBT); }
 }
 
 // grow-only scratch for the packed operand images (one learner = one stream; not shared across streams)
@@ -256,7 +297,7 @@ int launch_pack(const float* src, long long ld, int mn_lim, int k_lim, bool mn_m
 }  // namespace
 
 int gemm_tc_suggest_split_k(int M, int N, int K) {
-  long long tiles = (long long)ceil_div(M, TBM) * ceil_div(N, TBN);
+  long long tiles = (long long)ceil_div(M, TBM) * (N > TBN ? ceil_div(N, 2 * TBN) : 1);
   int k_tiles = ceil_div(K, TBK);
   if (tiles >= 2 * 148 || k_tiles < 16) return 1;
   int want = (int)ceil_div_ll(2 * 148, tiles);
@@ -270,7 +311,8 @@ int gemm_tc_suggest_split_k(int M, int N, int K) {
 int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    R2D2_CUDA_TRY(cudaFuncSetAttribute(gemm_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PACKED_GEMM_SMEM));
+    R2D2_CUDA_TRY(cudaFuncSetAttribute(gemm_packed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PackedCfg<1>::SMEM));
+    R2D2_CUDA_TRY(cudaFuncSetAttribute(gemm_packed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PackedCfg<2>::SMEM));
     attr_set = true;
   }
   const bool a_mn = (layout == GEMM_TN), b_mn = (layout != GEMM_NT);
@@ -297,8 +339,15 @@ int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   q.pa = p.A_img ? p.A_img : g_pack_a.ptr; q.pb = g_pack_b.ptr; q.k_tiles = k_tiles; q.C = p.C; q.ldc = p.ldc; q.M = p.M; q.N = p.N;
   q.bias = p.bias; q.Z = p.Z; q.ldz = p.ldz; q.epilogue = p.epilogue; q.split_k = p.split_k;
   q.a_mn = a_mn; q.b_mn = b_mn; q.debug_flags = p.debug_flags;
-  dim3 grid(n_tiles, m_tiles, p.split_k);
-  gemm_packed_kernel<<<grid, PACKED_GEMM_THREADS, PACKED_GEMM_SMEM, stream>>>(q);
+  static int force_nbt = -1;
+  if (force_nbt < 0) { const char* e = getenv("R2D2_GEMM_NBT"); force_nbt = e ? atoi(e) : 0; }
+  if (n_tiles > 1 && force_nbt != 1) {
+    dim3 grid(ceil_div(n_tiles, 2), m_tiles, p.split_k);
+    gemm_packed_kernel<2><<<grid, PACKED_GEMM_THREADS, PackedCfg<2>::SMEM, stream>>>(q);
+  } else {
+    dim3 grid(n_tiles, m_tiles, p.split_k);
+    gemm_packed_kernel<1><<<grid, PACKED_GEMM_THREADS, PackedCfg<1>::SMEM, stream>>>(q);
+  }
   count_launch();
   R2D2_CUDA_TRY(cudaGetLastError());
   return R2D2_OK;
