@@ -12,8 +12,10 @@ __device__ __forceinline__ float value_rescale(float x) {
   return x > 0.f ? m : (x < 0.f ? -m : 0.f);
 }
 
-// grid: ceil(B/32) CTAs, 256 threads = 8 warps; lane -> batch column, warp -> time rows i = w, w+8, ...
-__global__ void __launch_bounds__(256) td_priority_kernel(TdPriorityParams p) {
+// grid: ceil(B/32) CTAs, 1024 threads = 32 warps; lane -> batch column, warp -> time rows i = w, w+32, ...
+// (the kernel moves ~1 MB: it is bound by the length of the per-thread dependent load chain, hence the wide block)
+constexpr int TD_WARPS = 32;
+__global__ void __launch_bounds__(TD_WARPS * 32) td_priority_kernel(TdPriorityParams p) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = blockIdx.x * 32 + lane;
   const int L = p.L, B = p.B, A = p.A;
@@ -21,7 +23,7 @@ __global__ void __launch_bounds__(256) td_priority_kernel(TdPriorityParams p) {
   const float grad_scale = 2.0f / ((float)L * (float)B * (float)A);
   float run_max = -INFINITY, run_sum = 0.f, sq_total = 0.f;
   if (b < B) {
-    for (int i = w; i < L; i += 8) {
+    for (int i = w; i < L; i += TD_WARPS) {
       const float r = __ldg(p.rew + (size_t)(p.burn_in + i) * B + b);
       const float d = __ldg(p.term + (size_t)(p.burn_in + i + p.n_step - 1) * B + b);
       const float cont = p.gamma_n * (1.0f - d);
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(256) td_priority_kernel(TdPriorityParams p) {
       if (!(i == L - 1 && b == B - 1)) { run_max = fmaxf(run_max, td); run_sum += td; }
     }
   }
-  __shared__ float s_max[8][32], s_sum[8][32], s_sq[8];
+  __shared__ float s_max[TD_WARPS][32], s_sum[TD_WARPS][32], s_sq[TD_WARPS];
   s_max[w][lane] = run_max;
   s_sum[w][lane] = run_sum;
   const float wsq = warp_sum(sq_total);
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(256) td_priority_kernel(TdPriorityParams p) {
   if (w == 0) {
     float mx = s_max[0][lane], sm = s_sum[0][lane];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) { mx = fmaxf(mx, s_max[k][lane]); sm += s_sum[k][lane]; }
+    for (int k = 1; k < TD_WARPS; ++k) { mx = fmaxf(mx, s_max[k][lane]); sm += s_sum[k][lane]; }
     if (b < B && p.priority) {
       const int count = L - ((b == B - 1) ? 1 : 0);
       p.priority[b] = p.eta * mx + (1.0f - p.eta) * (sm / (float)count);  // utils.py:17-18
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(256) td_priority_kernel(TdPriorityParams p) {
     if (lane == 0 && p.loss_sum) {
       float tot = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) tot += s_sq[k];
+      for (int k = 0; k < TD_WARPS; ++k) tot += s_sq[k];
       atomicAdd(p.loss_sum, tot / ((float)L * (float)B * (float)A));
     }
   }
@@ -157,7 +159,7 @@ int td_priority(const TdPriorityParams& p, cudaStream_t stream) {
   R2D2_REQUIRE(p.q && p.q_next && p.rew && p.term, "null input");
   R2D2_REQUIRE(p.L > 0 && p.B > 0 && p.A > 0, "shape");
   if (p.loss_sum) R2D2_CUDA_TRY(cudaMemsetAsync(p.loss_sum, 0, sizeof(float), stream));
-  td_priority_kernel<<<ceil_div(p.B, 32), 256, 0, stream>>>(p);
+  td_priority_kernel<<<ceil_div(p.B, 32), TD_WARPS * 32, 0, stream>>>(p);
   count_launch();
   R2D2_CUDA_TRY(cudaGetLastError());
   return R2D2_OK;

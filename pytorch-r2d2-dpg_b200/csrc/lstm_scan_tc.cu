@@ -66,9 +66,9 @@ struct TcFwdSmem {
   static constexpr int RG_BYTES = C * SLICE;
   static constexpr int BUF_BYTES = RG * RG_BYTES;    // = NB * H * 4
   static constexpr int OFF_HB = 0;
+  static constexpr int NACC = (H / 16) < R2D2_SCAN_NACC ? (H / 16) : R2D2_SCAN_NACC;
   // tensor memory columns: NACC independent accumulators D_a at [a*NB, ..), then the W_hh slice: hi plane at 128
   // (H/2 columns: two bf16 per column), lo plane after it
-  static constexpr int NACC = (H / 16) < R2D2_SCAN_NACC ? (H / 16) : R2D2_SCAN_NACC;
   static constexpr int TM_A_HI = 128, TM_A_LO = 128 + H / 2, TM_COLS = 512;
   static constexpr int OFF_GT = OFF_HB + 2 * BUF_BYTES;            // fp32 [NB][GT_LD]
   static constexpr int OFF_HSTAGE = OFF_GT + NB * GT_LD * 4;       // [dbuf][row group][plane][4 chunks][8][16 B]
@@ -303,7 +303,6 @@ struct PpFwdSmem {
   static constexpr int RG_BYTES = C * SLICE;
   static constexpr int BUF_BYTES = 2 * RG_BYTES;          // 16 rows
   static constexpr int OFF_HB = 0;                        // [sub][buf][row group][slice][plane][4 chunks][8][16 B]
-  static constexpr int NACC = (H / 16) < R2D2_SCAN_NACC ? (H / 16) : R2D2_SCAN_NACC;
   static constexpr int TM_A_HI = 128, TM_A_LO = 128 + H / 2, TM_COLS = 512;   // D[sub][acc] at (sub*4 + acc)*16
   static constexpr int OFF_GT = OFF_HB + 4 * BUF_BYTES;   // fp32 [2 (iteration parity)][16][GT_LD]
   static constexpr int OFF_HSTAGE = OFF_GT + 2 * 16 * GT_LD * 4;   // [sub][step parity][row group][SLICE]
@@ -312,7 +311,7 @@ struct PpFwdSmem {
   static_assert(BYTES <= 232448, "ping-pong scan tile does not fit in shared memory");
 };
 
-template <int H>
+template <int H, bool TRACE>
 __global__ void __launch_bounds__(PP_THREADS, 1) lstm_scan_fwd_pp_kernel(ScanFwdParams p, int* err) {
   using SM = PpFwdSmem<H>;
   constexpr int C = SM::C, KC = SM::KC, KS = H / 16;
@@ -406,129 +405,153 @@ __global__ void __launch_bounds__(PP_THREADS, 1) lstm_scan_fwd_pp_kernel(ScanFwd
 
   const uint32_t hb_addr = tc::smem_u32(hb);
   const size_t gstride = (size_t)4 * H;
-  const int n_iter = n_sub * S;
+  const int n_iter = n_sub * S;   // trace slot index = s * n_sub + sub
+  // The loop bodies below are written per (cell step s, sub-tile `sub`) with `sub` a COMPILE-TIME index: the issue
+  // slots of this kernel went to index arithmetic (k % n_sub, s / repeat, 64-bit row addresses), not to the LSTM math
+  // (profiles/r01_summary.md), so everything that depends only on the sub-tile lives in registers and the global
+  // pointers advance by a constant per step.
+  const int rows_of[2] = {rows0, n_rows - rows0};
+  const int rgv_of[2] = {(rows0 + 7) >> 3, (n_rows - rows0 + 7) >> 3};
 
   if (w_u == PP_CELL_WARPS) {
     // ================= MMA warp =================
     const uint32_t idesc = tc::make_idesc_bf16_f32(128, 16);
     const uint64_t db0 = tc::make_smem_desc(hb_addr, 128, SM::RG_BYTES);
-    for (int k = 0; k < n_iter; ++k) {
-      const int sub = k % n_sub, s = k / n_sub;
+    for (int s = 0; s < S; ++s) {
       const int cur = s & 1, nxt = cur ^ 1;
-      const int rg_valid = (sub_rows(sub) + 7) >> 3;
-      if (s + 1 < S && tc::elect_one())
-        tc::mbar_arrive_expect_tx(&h_full[sub * 2 + nxt], (uint32_t)(C * rg_valid * SM::SLICE));
-      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 0] = gtime();
-      if (s > 0 && !*dead) {
-        if (!tc::mbar_wait(&h_full[sub * 2 + cur], ((s - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 5); }
-      }
-      __syncwarp();
-      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 1] = gtime();
-      tc::fence_after_thread_sync();
-      if (tc::elect_one()) {
-        const uint64_t db_cur = db0 + (uint64_t)(((sub * 2 + cur) * SM::BUF_BYTES) >> 4);
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          const uint32_t ta_hi = tmem_base + SM::TM_A_HI + ks * 8, ta_lo = tmem_base + SM::TM_A_LO + ks * 8;
-          const uint64_t db_hi = db_cur + (uint64_t)(((ks >> 1) * SM::SLICE + (ks & 1) * 256) >> 4);
-          const uint64_t db_lo = db_hi + (uint64_t)(512 >> 4);
-          const uint32_t d = tmem_base + (sub * 4 + (ks % SM::NACC)) * 16;
-          tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks >= SM::NACC);
-          tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
-          tc::mma_bf16_ts(d, ta_hi, db_hi, idesc, true);
+      for (int sub = 0; sub < 2; ++sub) {
+        if (sub >= n_sub) break;
+        if (s + 1 < S && tc::elect_one())
+          tc::mbar_arrive_expect_tx(&h_full[sub * 2 + nxt], (uint32_t)(C * rgv_of[sub] * SM::SLICE));
+        if (TRACE && lane == 0) p.trace[((size_t)blockIdx.x * n_iter + s * n_sub + sub) * 8 + 0] = gtime();
+        if (s > 0 && !*dead) {
+          if (!tc::mbar_wait(&h_full[sub * 2 + cur], ((s - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 5); }
         }
-        tc::mma_commit(&mma_done[sub]);
+        __syncwarp();
+        if (TRACE && lane == 0) p.trace[((size_t)blockIdx.x * n_iter + s * n_sub + sub) * 8 + 1] = gtime();
+        tc::fence_after_thread_sync();
+        if (tc::elect_one()) {
+          const uint64_t db_cur = db0 + (uint64_t)(((sub * 2 + cur) * SM::BUF_BYTES) >> 4);
+          const uint32_t d = tmem_base + sub * 64;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t ta_hi = tmem_base + SM::TM_A_HI + ks * 8, ta_lo = tmem_base + SM::TM_A_LO + ks * 8;
+            const uint64_t db_hi = db_cur + (uint64_t)(((ks >> 1) * SM::SLICE + (ks & 1) * 256) >> 4);
+            const uint64_t db_lo = db_hi + (uint64_t)(512 >> 4);
+            tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks != 0);
+            tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
+            tc::mma_bf16_ts(d, ta_hi, db_hi, idesc, true);
+          }
+          tc::mma_commit(&mma_done[sub]);
+        }
+        __syncwarp();
+        if (TRACE && lane == 0) p.trace[((size_t)blockIdx.x * n_iter + s * n_sub + sub) * 8 + 2] = gtime();
       }
-      __syncwarp();
-      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 2] = gtime();
     }
   } else {
     // ================= cell warps: warp w = row w of the current sub-tile, lane = hidden unit =================
     const int rg = w >> 3, r8 = w & 7;
-    float gq0[4], gq1[4];   // input projections of the next two iterations (prefetch distance 2: ~2 us of HBM latency cover)
-    auto prefetch = [&](int k, float (&dst)[4]) {
-      const int sub = k % n_sub, s = k / n_sub, t = s / p.repeat;
-      const bool on = k < n_iter && w < sub_rows(sub);
-      const int b = b0 + sub_row0(sub) + w;
+    const bool on_of[2] = {w < rows_of[0], n_sub == 2 && w < rows_of[1]};
+    // running pointers of this thread's (row, unit) in each sub-tile
+    const float* gin_next[2];     // gin row of step s + 1
+    float* gate_ptr[2];           // gates row of step s
+    float* hs_ptr[2];             // hs / cs row s + 1 (cs at the same offset from p.cs)
+    float* head_ptr[2];           // head_in row t
+    float gnx[2][4];              // prefetched input projection of this sub-tile's next step
 #pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = on ? p.gin[((size_t)t * B + b) * gstride + q * H + ug] : 0.f;
-    };
-    prefetch(0, gq0);
-    prefetch(1, gq1);
-    for (int k = 0; k < n_iter; ++k) {
-      const int sub = k % n_sub, s = k / n_sub, t = s / p.repeat;
-      const int nxt = (s & 1) ^ 1;
-      float gpre[4];
+    for (int sub = 0; sub < 2; ++sub) {
+      const size_t brow = (size_t)(b0 + (sub == 0 ? 0 : rows0) + w);
+      gate_ptr[sub] = p.gates + brow * gstride + ug;
+      hs_ptr[sub] = p.hs + ((size_t)B + brow) * H + ug;
+      head_ptr[sub] = p.head_in ? p.head_in + brow * H + ug : nullptr;
+      const float* g0 = p.gin + brow * gstride + ug;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { gpre[q] = gq0[q]; gq0[q] = gq1[q]; }
-      prefetch(k + 2, gq1);
-      if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 5] = gtime();
-      if (!*dead) {
-        if (!tc::mbar_wait(&mma_done[sub], s & 1)) { *dead = 1; atomicExch(err, 6); }
-      }
-      if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 3] = gtime();
-      tc::fence_after_thread_sync();
-      __syncwarp();
-      float* gt = gt_all + (k & 1) * 16 * GT_LD;
-      if ((w >> 2) < 2) {   // 8 warps read the 128 x 16 accumulators: lane quarter w&3, 8-column block w>>2
-        const int q = w & 3, c0 = (w >> 2) * 8;
-        float v[8];
-        tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64 + c0), v);
+      for (int q = 0; q < 4; ++q) gnx[sub][q] = on_of[sub] ? g0[q * H] : 0.f;
+      // row of step 1: the same input row while s + 1 < repeat
+      gin_next[sub] = (p.repeat > 1) ? g0 : g0 + (size_t)B * gstride;
+    }
+    const ptrdiff_t cs_off = p.cs - p.hs;
+    const size_t gate_step = (size_t)B * gstride, h_step = (size_t)B * H;
+    int rep = 0;                   // s % repeat
+    for (int s = 0; s < S; ++s) {
+      const int par = s & 1, nxt = par ^ 1;
+      const bool last_rep = rep == p.repeat - 1;
+      // after this step: rep' = (s + 1) % repeat; the input row of step s + 2 moves on when step s + 2 starts a new row
+      const int rep1 = last_rep ? 0 : rep + 1;
 #pragma unroll
-        for (int a = 1; a < SM::NACC; ++a) {
-          float u[8];
-          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64 + a * 16 + c0), u);
+      for (int sub = 0; sub < 2; ++sub) {
+        if (sub >= n_sub) break;
+        float gpre[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += u[j];
+        for (int q = 0; q < 4; ++q) gpre[q] = gnx[sub][q];
+        if (s + 1 < S && on_of[sub]) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gnx[sub][q] = gin_next[sub][q * H];
         }
+        if (TRACE && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + s * n_sub + sub) * 8 + 5] = gtime();
+        if (!*dead) {
+          if (!tc::mbar_wait(&mma_done[sub], par)) { *dead = 1; atomicExch(err, 6); }
+        }
+        if (TRACE && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + s * n_sub + sub) * 8 + 3] = gtime();
+        tc::fence_after_thread_sync();
+        __syncwarp();
+        float* gt = gt_all + (n_sub == 2 ? sub : par) * 16 * GT_LD;
+        if ((w >> 2) < 2) {   // 8 warps read the 128 x 16 accumulators: lane quarter w&3, 8-column block w>>2
+          const int q = w & 3, c0 = (w >> 2) * 8;
+          float v[8];
+          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64 + c0), v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gt[(c0 + j) * GT_LD + q * 32 + lane] = v[j];
-      }
-      tc::fence_before_thread_sync();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 4] = gtime();
+          for (int j = 0; j < 8; ++j) gt[(c0 + j) * GT_LD + q * 32 + lane] = v[j];
+        }
+        tc::fence_before_thread_sync();
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (TRACE && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + s * n_sub + sub) * 8 + 4] = gtime();
 
-      const int rows = sub_rows(sub);
-      const int rg_valid = (rows + 7) >> 3;
-      if (rg < rg_valid) {
-        unsigned char* hs_buf = hstage + ((sub * 2 + (s & 1)) * 2 + rg) * SM::SLICE;
-        __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
-        float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cn = 0.f, hn = 0.f;
-        const bool on = w < rows;
-        if (on) {
-          const float* gr = gt + w * GT_LD + lane;
-          ig = fast_sigmoid(gr[0] + gpre[0]);
-          fg = fast_sigmoid(gr[32] + gpre[1]);
-          gg = fast_tanh(gr[64] + gpre[2]);
-          og = fast_sigmoid(gr[96] + gpre[3]);
-          const float cprev = sub == 0 ? cst[0] : cst[1];
-          cn = fg * cprev + ig * gg;
-          hn = og * fast_tanh(cn);
-          if (sub == 0) cst[0] = cn; else cst[1] = cn;
-          split_bf16(hn, hi, lo);
+        if (rg < rgv_of[sub]) {
+          unsigned char* hs_buf = hstage + ((sub * 2 + par) * 2 + rg) * SM::SLICE;
+          __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+          float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cn = 0.f, hn = 0.f;
+          const bool on = on_of[sub];
+          if (on) {
+            const float* gr = gt + w * GT_LD + lane;
+            ig = fast_sigmoid(gr[0] + gpre[0]);
+            fg = fast_sigmoid(gr[32] + gpre[1]);
+            gg = fast_tanh(gr[64] + gpre[2]);
+            og = fast_sigmoid(gr[96] + gpre[3]);
+            cn = fg * cst[sub] + ig * gg;
+            hn = og * fast_tanh(cn);
+            cst[sub] = cn;
+            split_bf16(hn, hi, lo);
+          }
+          unsigned char* dst = hs_buf + (lane >> 3) * 128 + r8 * 16 + (lane & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(dst + 512) = lo;
+          tc::fence_proxy_async_smem();
+          if (rg == 0) asm volatile("bar.sync 2, 256;" ::: "memory");   // the 8 warps of this row group
+          else         asm volatile("bar.sync 3, 256;" ::: "memory");
+          if (s + 1 < S && r8 < C && tc::elect_one()) {
+            const uint32_t d = r8;
+            const uint32_t dst_local = hb_addr + (sub * 2 + nxt) * SM::BUF_BYTES + rg * SM::RG_BYTES + rank * SM::SLICE;
+            tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf), SM::SLICE,
+                                     tc::mapa(tc::smem_u32(&h_full[sub * 2 + nxt]), d));
+          }
+          if (on) {   // the saved activations leave AFTER the exchange has been started: they are off the serial chain
+            float* go = gate_ptr[sub];
+            go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
+            hs_ptr[sub][0] = hn;
+            hs_ptr[sub][cs_off] = cn;
+            if (head_ptr[sub] && last_rep) head_ptr[sub][0] = fast_tanh(hn);
+          }
         }
-        unsigned char* dst = hs_buf + (lane >> 3) * 128 + r8 * 16 + (lane & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(dst + 512) = lo;
-        tc::fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 256;" ::"r"(2 + rg) : "memory");   // the 8 warps of this row group
-        if (s + 1 < S && r8 < C && tc::elect_one()) {
-          const uint32_t d = r8;
-          const uint32_t dst_local = hb_addr + (sub * 2 + nxt) * SM::BUF_BYTES + rg * SM::RG_BYTES + rank * SM::SLICE;
-          tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf), SM::SLICE,
-                                   tc::mapa(tc::smem_u32(&h_full[sub * 2 + nxt]), d));
-        }
-        if (on) {   // the saved activations leave AFTER the exchange has been started: they are off the serial chain
-          const int b = b0 + sub_row0(sub) + w;
-          float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
-          go[0] = ig; go[H] = fg; go[2 * H] = gg; go[3 * H] = og;
-          p.hs[((size_t)(s + 1) * B + b) * H + ug] = hn;
-          p.cs[((size_t)(s + 1) * B + b) * H + ug] = cn;
-          if (p.head_in && (s % p.repeat) == p.repeat - 1)
-            p.head_in[((size_t)t * B + b) * H + ug] = fast_tanh(hn);
-        }
+        gate_ptr[sub] += gate_step;
+        hs_ptr[sub] += h_step;
+        if (last_rep && head_ptr[sub]) head_ptr[sub] += h_step;
+        // gin_next must point at the input row of step s + 2 = row (s + 2) / repeat
+        if (p.repeat == 1 || rep1 == p.repeat - 1) gin_next[sub] += gate_step;
+        if (TRACE && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + s * n_sub + sub) * 8 + 7] = gtime();
       }
-      if (p.trace && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + k) * 8 + 7] = gtime();
+      rep = rep1;
     }
   }
   tc::fence_before_thread_sync();
@@ -646,15 +669,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   const uint32_t slot_bytes = (uint32_t)n_valid * 128u;            // only rows that exist travel: [n][32 units] fp32
   const uint32_t step_tx = (uint32_t)C * slot_bytes;
 
-  for (int it = 0; it < S; ++it) {
-    const int s = S - 1 - it;
-    const int buf = it & 1;
-    const int t = s / p.repeat;
-    const int rel = s - p.head_first_step;
+  float pg[NT][4], pc_prev[NT], pc_new[NT], phead[NT];   // saved activations of the step being processed
+  {
+    const int s = S - 1, rel = s - p.head_first_step;
     const bool has_head = p.dh_head && rel >= 0 && (rel % p.repeat) == p.repeat - 1;
-
-    // prefetch the saved activations of this step before waiting for the partial sums
-    float pg[NT][4], pc_prev[NT], pc_new[NT], phead[NT];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int b = b0 + 8 * (half + 2 * j) + r8;
@@ -668,6 +686,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
         pc_prev[j] = __ldg(p.cs + ((size_t)s * B + b) * H + ug);
         pc_new[j] = __ldg(p.cs + ((size_t)(s + 1) * B + b) * H + ug);
         if (has_head) phead[j] = __ldg(p.dh_head + ((size_t)(rel / p.repeat) * B + b) * H + ug);
+      }
+    }
+  }
+
+  for (int it = 0; it < S; ++it) {
+    const int s = S - 1 - it;
+    const int buf = it & 1;
+    const int t = s / p.repeat;
+
+    // software pipeline of the saved activations: the operands of THIS step were loaded one step ago (an HBM round
+    // trip is ~half a cell step and used to sit on the serial chain); now fetch the ones of step s-1.
+    // cs[s] is c_prev of this step and c_new of the next one, so only one new cell state per step.
+    float ng[NT][4], nc[NT], nh[NT];
+    {
+      const int sn = s - 1;
+      const int reln = sn - p.head_first_step;
+      const bool head_n = p.dh_head && reln >= 0 && (reln % p.repeat) == p.repeat - 1;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int b = b0 + 8 * (half + 2 * j) + r8;
+        nc[j] = nh[j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ng[j][q] = 0.f;
+        if (sn >= 0 && b < b_end) {
+          const float* gs = p.gates + ((size_t)sn * B + b) * gstride + ug;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ng[j][q] = gs[q * H];
+          nc[j] = __ldg(p.cs + ((size_t)sn * B + b) * H + ug);
+          if (head_n) nh[j] = __ldg(p.dh_head + ((size_t)(reln / p.repeat) * B + b) * H + ug);
+        }
       }
     }
     if (it > 0 && !*dead) {
@@ -843,6 +891,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       const uint32_t dst_local = tc::smem_u32(ps + ((size_t)((buf ^ 1) * C + rank) * NB) * 32);
       tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, slot_bytes, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
     }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {   // rotate the pipeline registers
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pg[j][q] = ng[j][q];
+      pc_new[j] = pc_prev[j];
+      pc_prev[j] = nc[j];
+      phead[j] = nh[j];
+    }
   }
   tc::fence_before_thread_sync();
   cluster.sync();
@@ -940,7 +996,8 @@ int fwd_tc(const ScanFwdParams& p_in, cudaStream_t stream) {
   if (t.nb == 16)
     return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 16>, p, H / 32, t.n_clusters, TcFwdSmem<H, 16>::BYTES, stream);
   if (scan_pingpong_enabled())
-    return launch_cluster_tc(lstm_scan_fwd_pp_kernel<H>, p, H / 32, t.n_clusters, PpFwdSmem<H>::BYTES, stream, PP_THREADS);
+    return p.trace ? launch_cluster_tc(lstm_scan_fwd_pp_kernel<H, true>, p, H / 32, t.n_clusters, PpFwdSmem<H>::BYTES, stream, PP_THREADS)
+                   : launch_cluster_tc(lstm_scan_fwd_pp_kernel<H, false>, p, H / 32, t.n_clusters, PpFwdSmem<H>::BYTES, stream, PP_THREADS);
   return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 32>, p, H / 32, t.n_clusters, TcFwdSmem<H, 32>::BYTES, stream);
 }
 template <int H>
