@@ -669,60 +669,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   const uint32_t slot_bytes = (uint32_t)n_valid * 128u;            // only rows that exist travel: [n][32 units] fp32
   const uint32_t step_tx = (uint32_t)C * slot_bytes;
 
+  // ---- per-thread constants and running pointers (index arithmetic, not LSTM math, dominated the issue slots of this
+  // loop: no division, no 64-bit row address is recomputed per step)
+  bool rowon[NT];
+  const float* gates_nx[NT];    // gates row of the step that is prefetched next (s - 1)
+  const float* cs_nx[NT];       // cs row s - 1
+  const float* head_nx[NT];     // dh_head row consumed at step s - 1 (valid while hrow_nx >= 0)
+  const size_t g_step = (size_t)B * gstride, h_step = (size_t)B * H;
+  // head gradient bookkeeping for the step being prefetched: rel = s' - head_first_step, relm = rel % repeat,
+  // consumed when rel >= 0 and relm == repeat - 1
+  int rel_nx = (S - 1) - p.head_first_step;
+  int relm_nx = rel_nx >= 0 ? rel_nx % p.repeat : 0;
+  // first head row that will be consumed: the largest rel' <= rel with rel' % repeat == repeat - 1
+  const int hrow0 = rel_nx >= 0 ? (rel_nx / p.repeat - (relm_nx == p.repeat - 1 ? 0 : 1)) : 0;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int b = b0 + 8 * (half + 2 * j) + r8;
+    rowon[j] = b < b_end;
+    const size_t bb = rowon[j] ? (size_t)b : (size_t)b0;
+    gates_nx[j] = p.gates + ((size_t)(S - 1) * B + bb) * gstride + ug;
+    cs_nx[j] = p.cs + ((size_t)(S - 1) * B + bb) * H + ug;
+    head_nx[j] = (p.dh_head && hrow0 >= 0) ? p.dh_head + ((size_t)hrow0 * B + bb) * H + ug : nullptr;
+  }
   float pg[NT][4], pc_prev[NT], pc_new[NT], phead[NT];   // saved activations of the step being processed
-  {
-    const int s = S - 1, rel = s - p.head_first_step;
-    const bool has_head = p.dh_head && rel >= 0 && (rel % p.repeat) == p.repeat - 1;
+  auto fetch = [&](float (&g)[NT][4], float (&c)[NT], float (&hd)[NT], bool any) {
+    const bool head_now = head_nx[0] != nullptr && rel_nx >= 0 && relm_nx == p.repeat - 1;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      const int b = b0 + 8 * (half + 2 * j) + r8;
-      pc_prev[j] = pc_new[j] = phead[j] = 0.f;
+      c[j] = hd[j] = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) pg[j][q] = 0.f;
-      if (b < b_end) {
-        const float* gs = p.gates + ((size_t)s * B + b) * gstride + ug;
+      for (int q = 0; q < 4; ++q) g[j][q] = 0.f;
+      if (any && rowon[j]) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) pg[j][q] = gs[q * H];
-        pc_prev[j] = __ldg(p.cs + ((size_t)s * B + b) * H + ug);
-        pc_new[j] = __ldg(p.cs + ((size_t)(s + 1) * B + b) * H + ug);
-        if (has_head) phead[j] = __ldg(p.dh_head + ((size_t)(rel / p.repeat) * B + b) * H + ug);
+        for (int q = 0; q < 4; ++q) g[j][q] = gates_nx[j][q * H];
+        c[j] = __ldg(cs_nx[j]);
+        if (head_now) hd[j] = __ldg(head_nx[j]);
       }
+      gates_nx[j] -= g_step;
+      cs_nx[j] -= h_step;
+      if (head_now) head_nx[j] -= h_step;
     }
-  }
+    // advance the bookkeeping to the next older step
+    --rel_nx;
+    relm_nx = relm_nx == 0 ? p.repeat - 1 : relm_nx - 1;
+  };
+#pragma unroll
+  for (int j = 0; j < NT; ++j) pc_new[j] = rowon[j] ? __ldg(cs_nx[j] + h_step) : 0.f;   // cs[S]
+  fetch(pg, pc_prev, phead, true);
 
+  int rep = (S - 1) % p.repeat, t = (S - 1) / p.repeat;   // s % repeat and s / repeat, kept by counting
   for (int it = 0; it < S; ++it) {
     const int s = S - 1 - it;
     const int buf = it & 1;
-    const int t = s / p.repeat;
 
     // software pipeline of the saved activations: the operands of THIS step were loaded one step ago (an HBM round
     // trip is ~half a cell step and used to sit on the serial chain); now fetch the ones of step s-1.
     // cs[s] is c_prev of this step and c_new of the next one, so only one new cell state per step.
     float ng[NT][4], nc[NT], nh[NT];
-    {
-      const int sn = s - 1;
-      const int reln = sn - p.head_first_step;
-      const bool head_n = p.dh_head && reln >= 0 && (reln % p.repeat) == p.repeat - 1;
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const int b = b0 + 8 * (half + 2 * j) + r8;
-        nc[j] = nh[j] = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ng[j][q] = 0.f;
-        if (sn >= 0 && b < b_end) {
-          const float* gs = p.gates + ((size_t)sn * B + b) * gstride + ug;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) ng[j][q] = gs[q * H];
-          nc[j] = __ldg(p.cs + ((size_t)sn * B + b) * H + ug);
-          if (head_n) nh[j] = __ldg(p.dh_head + ((size_t)(reln / p.repeat) * B + b) * H + ug);
-        }
-      }
-    }
+    fetch(ng, nc, nh, s > 0);
     if (it > 0 && !*dead) {
       if (!tc::mbar_wait(&ps_full[buf], ((it - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 3); }
     }
 
-    const bool emit_gin = p.repeat > 1 && (s % p.repeat == 0);
+    const bool emit_gin = p.repeat > 1 && rep == 0;
     // ---- pointwise backward of the cell (thread = (unit = lane, row r8 of row group e)); the dG values go to the MMA
     // operand tile first - their HBM copies are written below, after the tensor-core step has been started
     float dgr[NT][4];
@@ -899,6 +908,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       pc_prev[j] = nc[j];
       phead[j] = nh[j];
     }
+    if (rep == 0) { rep = p.repeat - 1; --t; } else --rep;
   }
   tc::fence_before_thread_sync();
   cluster.sync();
