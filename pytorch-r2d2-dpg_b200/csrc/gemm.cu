@@ -257,6 +257,10 @@ static int g_skinny_mma = 1;
 void gemm_set_impl_skinny_mma(int on) { g_skinny_mma = on ? 1 : 0; }
 int gemm_get_impl_skinny_mma() { return g_skinny_mma; }
 
+bool gemm_emits_operand_image(int N, int K_total) {
+  return gemm_get_impl() == 1 && gemm_get_impl_skinny_mma() && K_total <= 32 && N > 32 && N % 32 == 0;
+}
+
 int gemm_suggest_split_k(int M, int N, int K) {
   const bool skinny = (K < 64) || (N < 32) || (M < 32);
   if (gemm_get_impl() == 1 && !(skinny && g_skinny_mma)) return gemm_tc_suggest_split_k(M, N, K);
@@ -292,6 +296,7 @@ int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
     R2D2_TRY(gemm_thin_try(p, layout, stream, &handled));
     if (handled) return R2D2_OK;
   }
+  R2D2_REQUIRE(!p.C_img_k, "C_img_k is only produced by the small-K streaming kernel (see gemm_emits_operand_image)");
   if (gemm_get_impl() == 1 && !(skinny && gemm_get_impl_skinny_mma())) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("R2D2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }

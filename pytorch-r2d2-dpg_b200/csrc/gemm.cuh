@@ -34,12 +34,16 @@ struct GemmParams {
   int split_k = 1;           // >1: partial products are atomically added into C (C must be pre-zeroed)
   const unsigned char* A_img = nullptr;   // tcgen05 path: A already in packed tile-major form (gemm_tc.cu image of this
                              // call's layout and tiling, e.g. written by the BPTT scan); A / lda are ignored
+  unsigned char* C_img_k = nullptr;      // small-K kernel only (gemm_thin.cu): also write C as the K-major packed operand image
+                             // [ceil(M/128)][N/32][16 KB] for a following product that contracts over N
   int reuse_packed_a = 0;    // tcgen05 path: A (pointer, shape, layout) is the operand the previous gemm_f32 call packed
                              // and its contents have not changed since -> skip the pack pass (dW_hh then dW_ih of a chain)
   int debug_flags = 0;       // dev only (env R2D2_GEMM_DEBUG): 1 = producers skip fetch+convert, 2 = skip MMAs, 4 = skip epilogue stores
 };
 
 int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream);
+// true when gemm_f32 will honour GemmParams::C_img_k for an NT product with these sizes (small-K streaming kernel selected)
+bool gemm_emits_operand_image(int N, int K_total);
 // picks a split-K factor so that a skinny-output wgrad GEMM fills the 148 SMs
 int gemm_suggest_split_k(int M, int N, int K);
 

@@ -131,6 +131,50 @@ __global__ void __launch_bounds__(SK_THREADS) thin_smallk_kernel(GemmParams p, i
 #pragma unroll
           for (int j = 0; j < 4; ++j) if (col + j < p.N) cp[j] = v[j];
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = v[j];   // keep the finished values for the image below
+      }
+    }
+    if (p.C_img_k) {
+      // C also leaves as the K-major bf16 hi/lo operand image of the product that consumes it next (gemm_tc.cu tile
+      // format, K = N of this call): lanes 2i / 2i+1 hold the two halves of an 8-column chunk, so they swap rows
+      // (even lane ends with rows 0-3 x 8 columns, odd lane with rows 4-7) and write 32-byte pieces = two rows of a
+      // core matrix with one 256-bit store each.
+      const bool odd = (tid & 1) != 0;
+      float own[4][4], oth[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float send = odd ? acc[i][j] : acc[4 + i][j];
+          oth[i][j] = __shfl_xor_sync(0xffffffffu, send, 1);
+          own[i][j] = odd ? acc[4 + i][j] : acc[i][j];
+        }
+      const int m0 = r0 + rgp * 8;
+      const int c8 = col >> 3;
+      if (col < p.N) {
+        unsigned char* base = p.C_img_k + ((size_t)(m0 >> 7) * (p.N >> 5) + (c8 >> 2)) * 16384 +
+                              ((((m0 & 127) >> 3) * 32) + (c8 & 3) * 8) * 16 + (odd ? 64 : 0);
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {     // row pairs (0,1) and (2,3) of this lane's four rows
+          float hi8[8], lo8[8];
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int i = 2 * pr + rr;
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { x[j] = odd ? oth[i][j] : own[i][j]; x[4 + j] = odd ? own[i][j] : oth[i][j]; }
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_pack2(x[2 * j], x[2 * j + 1], h[j], l[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { hi8[rr * 4 + j] = __uint_as_float(h[j]); lo8[rr * 4 + j] = __uint_as_float(l[j]); }
+          }
+          if (m0 + (odd ? 4 : 0) + 2 * pr < p.M) {       // rows past M only feed masked output rows of the consumer
+            st_global_v8(reinterpret_cast<float*>(base + pr * 32), hi8);
+            st_global_v8(reinterpret_cast<float*>(base + 8192 + pr * 32), lo8);
+          }
+        }
       }
     }
     cp_async_wait_all();
@@ -331,6 +375,7 @@ int gemm_thin_try(const GemmParams& p, GemmLayout layout, cudaStream_t stream, b
     return nn ? launch_thin_smalln<true, 32>(p, stream) : launch_thin_smalln<false, 32>(p, stream);
   }
   if (p.K + p.K2 <= SK_KMAX && (p.K2 == 0 || !nn)) {
+    R2D2_REQUIRE(!p.C_img_k || (p.N % 32 == 0), "operand image needs N % 32 == 0");
     *handled = true;
     const int row_tiles = ceil_div(p.M, SK_ROWS), ny = ceil_div(p.N, SK_COLS);
     int gx = 444 / ny;                                 // 3 resident blocks per SM (registers)

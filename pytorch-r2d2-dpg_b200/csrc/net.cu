@@ -64,11 +64,16 @@ int net_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, const 
   const int H = s.hidden, O = s.obs, A = s.act, I = s.in_features();
   const int M = T * B;
   R2D2_REQUIRE(!s.critic || act != nullptr, "critic needs actions");
+  bool z1_img = false;
   {  // z1 = tanh(x * W1^T + b1)   (models.py:33 / :75-76; cat(obs, act) as two K segments)
     GemmParams g;
     g.A = obs; g.lda = O; g.B = P.w1; g.ldb = I; g.K = O;
     if (s.critic) { g.A2 = act; g.lda2 = A; g.B2 = P.w1 + O; g.ldb2 = I; g.K2 = A; }
     g.C = ws.z1; g.ldc = H; g.M = M; g.N = H; g.bias = P.b1; g.epilogue = EPI_TANH;
+    // the l1 kernel can write z1 a second time as the packed A operand of the W_ih product (the BPTT image buffer is
+    // idle during the forward pass)
+    z1_img = ws.img_k != nullptr && gemm_emits_operand_image(H, I);
+    if (z1_img) g.C_img_k = ws.img_k;
     R2D2_TRY(gemm_f32(g, GEMM_NT, stream));
   }
   R2D2_TRY(add_vec(P.bih, P.bhh, ws.bias_sum, 4 * H, stream));
@@ -76,6 +81,7 @@ int net_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, const 
     GemmParams g;
     g.A = ws.z1; g.lda = H; g.B = P.wih; g.ldb = H; g.K = H;
     g.C = ws.gin; g.ldc = 4 * H; g.M = M; g.N = 4 * H; g.bias = ws.bias_sum;
+    if (z1_img) g.A_img = ws.img_k;
     R2D2_TRY(gemm_f32(g, GEMM_NT, stream));
   }
   ScanFwdParams sp;
