@@ -43,6 +43,18 @@ const char* last_error();
 void count_launch(int n = 1);
 long long launch_count();
 
+// once-per-device guard for cudaFuncSetAttribute calls (function attributes are per device; a process may drive several)
+struct PerDeviceOnce {
+  unsigned long long done = 0;   // bit d set: already done on device d (d < 64); benign race: the call is idempotent
+  bool need() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done & (1ull << dev)) return false;
+    done |= (1ull << dev);
+    return true;
+  }
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

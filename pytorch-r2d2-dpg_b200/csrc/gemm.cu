@@ -224,11 +224,10 @@ gemm_bf16x3_kernel(GemmParams p, int vecA, int vecB, int vecA2, int vecB2) {
 template <int LAYOUT>
 int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using G = TileGeom<LAYOUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     R2D2_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16x3_kernel<LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        G::SMEM_BYTES));
-    attr_set = true;
   }
   auto aligned = [](const float* ptr, long long ld) {
     return ptr != nullptr && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && (ld % 4 == 0);

@@ -14,6 +14,10 @@
 // count as the fp32 operand and is re-read ~N/128 (A) or ~M/128 (B) times from L2.
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "gemm.cuh"
 #include "tc05.cuh"
 
@@ -270,9 +274,22 @@ __global__ void __launch_bounds__(PACKED_GEMM_THREADS, 2) gemm_packed_kernel(Pac
   if (w_u == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, TBN * NBT); }
 }
 
-// grow-only scratch for the packed operand images (one learner = one stream; not shared across streams)
+// grow-only scratch for the packed operand images, one set per (device, stream): kernels of one stream are ordered,
+// so a pack pass and the GEMM that reads it never overlap with the next call's pack on the same buffers; different
+// streams (other learners, other devices, other host threads) never share a buffer.
 struct Scratch { unsigned char* ptr = nullptr; size_t bytes = 0; };
-Scratch g_pack_a, g_pack_b;
+struct LastPackedA { const float* ptr = nullptr; long long ld = 0; int mn = 0, k = 0, mn_major = 0, k_tiles = 0; };
+struct StreamScratch { Scratch a, b; LastPackedA last_a; };
+std::mutex g_scratch_mutex;
+std::map<std::pair<int, cudaStream_t>, StreamScratch> g_scratch;
+
+int scratch_for(cudaStream_t stream, StreamScratch** out) {
+  int dev = 0;
+  R2D2_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_scratch_mutex);
+  *out = &g_scratch[std::make_pair(dev, stream)];   // std::map: references stay valid across insertions
+  return R2D2_OK;
+}
 
 int ensure_scratch(Scratch& s, size_t bytes) {
   if (s.bytes >= bytes) return R2D2_OK;
@@ -309,25 +326,28 @@ int gemm_tc_suggest_split_k(int M, int N, int K) {
 }
 
 int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     R2D2_CUDA_TRY(cudaFuncSetAttribute(gemm_packed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PackedCfg<1>::SMEM));
     R2D2_CUDA_TRY(cudaFuncSetAttribute(gemm_packed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PackedCfg<2>::SMEM));
-    attr_set = true;
   }
   const bool a_mn = (layout == GEMM_TN), b_mn = (layout != GEMM_NT);
   const int m_tiles = ceil_div(p.M, TBM), n_tiles = ceil_div(p.N, TBN);
   const int kt1 = ceil_div(p.K, TBK), kt2 = p.K2 > 0 ? ceil_div(p.K2, TBK) : 0;
   const int k_tiles = kt1 + kt2;
+  StreamScratch* sc = nullptr;
+  R2D2_TRY(scratch_for(stream, &sc));
+  Scratch& g_pack_a = sc->a;
+  Scratch& g_pack_b = sc->b;
+  LastPackedA& last_a = sc->last_a;
   if (!p.A_img) R2D2_TRY(ensure_scratch(g_pack_a, (size_t)m_tiles * k_tiles * TILE_BYTES));
   R2D2_TRY(ensure_scratch(g_pack_b, (size_t)n_tiles * k_tiles * TILE_BYTES));
-  // key of the image currently held in g_pack_a: reuse is honoured only if the caller asks AND the key matches
-  static struct { const float* ptr; long long ld; int mn, k, mn_major, k_tiles; cudaStream_t stream; } last_a = {};
+  // key of the image currently held in the A scratch: reuse is honoured only if the caller asks AND the key matches
   const bool reuse = p.reuse_packed_a && kt2 == 0 && last_a.ptr == p.A && last_a.ld == p.lda && last_a.mn == p.M &&
-                     last_a.k == p.K && last_a.mn_major == (a_mn ? 1 : 0) && last_a.k_tiles == k_tiles && last_a.stream == stream;
+                     last_a.k == p.K && last_a.mn_major == (a_mn ? 1 : 0) && last_a.k_tiles == k_tiles;
   if (!p.A_img) {
     if (!reuse) R2D2_TRY(launch_pack(p.A, p.lda, p.M, p.K, a_mn, m_tiles, k_tiles, 0, g_pack_a.ptr, stream));
-    last_a = {kt2 ? nullptr : p.A, p.lda, p.M, p.K, a_mn ? 1 : 0, k_tiles, stream};
+    last_a = LastPackedA{kt2 ? nullptr : p.A, p.lda, p.M, p.K, a_mn ? 1 : 0, k_tiles};
   }
   R2D2_TRY(launch_pack(p.B, p.ldb, p.N, p.K, b_mn, n_tiles, k_tiles, 0, g_pack_b.ptr, stream));
   if (kt2) {

@@ -332,11 +332,8 @@ template <bool NN, int NP>
 int launch_thin_smalln(const GemmParams& p, cudaStream_t stream) {
   const int kpad = ceil_div(p.K, 128) * 128;
   const size_t smem = (size_t)NP * kpad * sizeof(float);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+  if (smem > 48 * 1024)   // rare (N = 32 with K > 384): not worth caching per device
     R2D2_CUDA_TRY(cudaFuncSetAttribute(thin_smalln_kernel<NN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
   const int groups = ceil_div(p.M, 32 / NP);
   int grid = ceil_div(groups, SN_THREADS / 32);
   if (grid > 148 * 6) grid = 148 * 6;

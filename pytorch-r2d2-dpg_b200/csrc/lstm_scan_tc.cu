@@ -16,6 +16,9 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+
 #include "lstm_scan.cuh"
 #include "tc05.cuh"
 
@@ -1038,12 +1041,18 @@ int bwd_tc(const ScanBwdParams& p_in, cudaStream_t stream) {
 
 }  // namespace
 
-int* scan_error_flag() {
-  static int* flag = nullptr;
-  if (!flag) {
-    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(flag, 0, sizeof(int));
-  }
+int* scan_error_flag() {   // one flag per device (a process may drive several GPUs through separate handles)
+  static std::mutex mu;
+  static std::map<int, int*> flags;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = flags.find(dev);
+  if (it != flags.end()) return it->second;
+  int* flag = nullptr;
+  if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+  cudaMemset(flag, 0, sizeof(int));
+  flags[dev] = flag;
   return flag;
 }
 
