@@ -500,15 +500,16 @@ __global__ void __launch_bounds__(PP_THREADS, 1) lstm_scan_fwd_pp_kernel(ScanFwd
         tc::fence_after_thread_sync();
         __syncwarp();
         float* gt = gt_all + (n_sub == 2 ? sub : par) * 16 * GT_LD;
-        if ((w >> 2) < 2) {   // 8 warps read the 128 x 16 accumulators: lane quarter w&3, 8-column block w>>2
-          const int q = w & 3, c0 = (w >> 2) * 8;
+        if ((w & 7) < 4) {    // the first 4 warps of each row group read that group's 8 accumulator columns (lane quarter
+          const int q = w & 3, c0 = rg * 8;   // = warp % 4): the two row groups never wait for each other
           float v[8];
           tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64 + c0), v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) gt[(c0 + j) * GT_LD + q * 32 + lane] = v[j];
         }
         tc::fence_before_thread_sync();
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (rg == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+        else         asm volatile("bar.sync 3, 256;" ::: "memory");
         if (TRACE && tid == 0) p.trace[((size_t)blockIdx.x * n_iter + s * n_sub + sub) * 8 + 4] = gtime();
 
         if (rg < rgv_of[sub]) {

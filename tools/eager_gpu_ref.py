@@ -15,6 +15,8 @@ if __name__ == "__main__":
     torch.set_default_device(dev)                    # modules, zero states and optim state are created on the GPU
     lr = ref_port.PortLearner(pc, seed=1)
     torch.set_default_device("cpu")
+    for name in ("actor", "target_actor", "critic", "target_critic"):   # parameters built from numpy land on the CPU
+        getattr(lr, name).to(dev)
     def _advance(self, x):
         z = torch.tanh(self.l1(x))
         if self.hx is None:
