@@ -275,8 +275,8 @@ int gemm_suggest_split_k(int M, int N, int K) {
 }
 
 int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
-  R2D2_REQUIRE((p.A || p.A_img) && p.B && p.C, "null operand");
-  if (p.A_img) {
+  R2D2_REQUIRE((p.A || p.A_img) && (p.B || p.B_img) && p.C, "null operand");
+  if (p.A_img || p.B_img) {
     R2D2_REQUIRE(p.K2 == 0, "packed A with a second K segment");
     return gemm_f32_tc(p, layout, stream);
   }
@@ -295,7 +295,7 @@ int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
     R2D2_TRY(gemm_thin_try(p, layout, stream, &handled));
     if (handled) return R2D2_OK;
   }
-  R2D2_REQUIRE(!p.C_img_k, "C_img_k is only produced by the small-K streaming kernel (see gemm_emits_operand_image)");
+  R2D2_REQUIRE(!p.C_img_k && !p.C_img_mn, "C_img_* is only produced by the small-K streaming kernel (see gemm_emits_operand_image)");
   if (gemm_get_impl() == 1 && !(skinny && gemm_get_impl_skinny_mma())) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("R2D2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }

@@ -36,6 +36,9 @@ struct GemmParams {
                              // call's layout and tiling, e.g. written by the BPTT scan); A / lda are ignored
   unsigned char* C_img_k = nullptr;      // small-K kernel only (gemm_thin.cu): also write C as the K-major packed operand image
                              // [ceil(M/128)][N/32][16 KB] for a following product that contracts over N
+  unsigned char* C_img_mn = nullptr;     // same, MN-major image [ceil(N/128)][ceil(M/32)][16 KB]: C as the B operand of a TN
+                             // product that contracts over C's rows (z1 in dW_ih)
+  const unsigned char* B_img = nullptr;   // tcgen05 path: B already packed (image of this call's layout and tiling)
   int reuse_packed_a = 0;    // tcgen05 path: A (pointer, shape, layout) is the operand the previous gemm_f32 call packed
                              // and its contents have not changed since -> skip the pack pass (dW_hh then dW_ih of a chain)
   int debug_flags = 0;       // dev only (env R2D2_GEMM_DEBUG): 1 = producers skip fetch+convert, 2 = skip MMAs, 4 = skip epilogue stores

@@ -341,7 +341,7 @@ int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   Scratch& g_pack_b = sc->b;
   LastPackedA& last_a = sc->last_a;
   if (!p.A_img) R2D2_TRY(ensure_scratch(g_pack_a, (size_t)m_tiles * k_tiles * TILE_BYTES));
-  R2D2_TRY(ensure_scratch(g_pack_b, (size_t)n_tiles * k_tiles * TILE_BYTES));
+  if (!p.B_img) R2D2_TRY(ensure_scratch(g_pack_b, (size_t)n_tiles * k_tiles * TILE_BYTES));
   // key of the image currently held in the A scratch: reuse is honoured only if the caller asks AND the key matches
   const bool reuse = p.reuse_packed_a && kt2 == 0 && last_a.ptr == p.A && last_a.ld == p.lda && last_a.mn == p.M &&
                      last_a.k == p.K && last_a.mn_major == (a_mn ? 1 : 0) && last_a.k_tiles == k_tiles;
@@ -349,19 +349,22 @@ int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
     if (!reuse) R2D2_TRY(launch_pack(p.A, p.lda, p.M, p.K, a_mn, m_tiles, k_tiles, 0, g_pack_a.ptr, stream));
     last_a = LastPackedA{kt2 ? nullptr : p.A, p.lda, p.M, p.K, a_mn ? 1 : 0, k_tiles};
   }
-  R2D2_TRY(launch_pack(p.B, p.ldb, p.N, p.K, b_mn, n_tiles, k_tiles, 0, g_pack_b.ptr, stream));
+  if (!p.B_img) R2D2_TRY(launch_pack(p.B, p.ldb, p.N, p.K, b_mn, n_tiles, k_tiles, 0, g_pack_b.ptr, stream));
   if (kt2) {
-    R2D2_REQUIRE(!p.A_img, "packed A with a second K segment");
+    R2D2_REQUIRE(!p.A_img && !p.B_img, "packed operand with a second K segment");
     R2D2_TRY(launch_pack(p.A2, p.lda2, p.M, p.K2, a_mn, m_tiles, k_tiles, kt1, g_pack_a.ptr, stream));
     R2D2_TRY(launch_pack(p.B2, p.ldb2, p.N, p.K2, b_mn, n_tiles, k_tiles, kt1, g_pack_b.ptr, stream));
   }
   PackedGemmParams q;
-  q.pa = p.A_img ? p.A_img : g_pack_a.ptr; q.pb = g_pack_b.ptr; q.k_tiles = k_tiles; q.C = p.C; q.ldc = p.ldc; q.M = p.M; q.N = p.N;
+  q.pa = p.A_img ? p.A_img : g_pack_a.ptr; q.pb = p.B_img ? p.B_img : g_pack_b.ptr; q.k_tiles = k_tiles; q.C = p.C; q.ldc = p.ldc; q.M = p.M; q.N = p.N;
   q.bias = p.bias; q.Z = p.Z; q.ldz = p.ldz; q.epilogue = p.epilogue; q.split_k = p.split_k;
   q.a_mn = a_mn; q.b_mn = b_mn; q.debug_flags = p.debug_flags;
   static int force_nbt = -1;
   if (force_nbt < 0) { const char* e = getenv("R2D2_GEMM_NBT"); force_nbt = e ? atoi(e) : 0; }
-  if (n_tiles > 1 && force_nbt != 1) {
+  // two B tiles per CTA when the A images would otherwise be re-read many times (N >= 512) or the CTA count is set by
+  // split-K anyway; a 256-wide product with a long K keeps 128-wide tiles (twice the CTAs: measured 52 vs 58 us)
+  const bool wide = n_tiles > 1 && (n_tiles >= 4 || p.split_k > 1);
+  if ((wide && force_nbt != 1) || (n_tiles > 1 && force_nbt == 2)) {
     dim3 grid(ceil_div(n_tiles, 2), m_tiles, p.split_k);
     gemm_packed_kernel<2><<<grid, PACKED_GEMM_THREADS, PackedCfg<2>::SMEM, stream>>>(q);
   } else {

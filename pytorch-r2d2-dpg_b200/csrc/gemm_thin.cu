@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(SK_THREADS) thin_smallk_kernel(GemmParams p, i
         for (int j = 0; j < 4; ++j) acc[r][j] = v[j];   // keep the finished values for the image below
       }
     }
-    if (p.C_img_k) {
+    if (p.C_img_k || p.C_img_mn) {
       // C also leaves as the K-major bf16 hi/lo operand image of the product that consumes it next (gemm_tc.cu tile
       // format, K = N of this call): lanes 2i / 2i+1 hold the two halves of an 8-column chunk, so they swap rows
       // (even lane ends with rows 0-3 x 8 columns, odd lane with rows 4-7) and write 32-byte pieces = two rows of a
@@ -153,8 +153,11 @@ __global__ void __launch_bounds__(SK_THREADS) thin_smallk_kernel(GemmParams p, i
       const int m0 = r0 + rgp * 8;
       const int c8 = col >> 3;
       if (col < p.N) {
-        unsigned char* base = p.C_img_k + ((size_t)(m0 >> 7) * (p.N >> 5) + (c8 >> 2)) * 16384 +
-                              ((((m0 & 127) >> 3) * 32) + (c8 & 3) * 8) * 16 + (odd ? 64 : 0);
+        unsigned char* base = p.C_img_k ? p.C_img_k + ((size_t)(m0 >> 7) * (p.N >> 5) + (c8 >> 2)) * 16384 +
+                                              ((((m0 & 127) >> 3) * 32) + (c8 & 3) * 8) * 16 + (odd ? 64 : 0) : nullptr;
+        // MN-major twin (rows = reduction index): tile (col / 128, row / 32), same 16-byte chunks
+        unsigned char* base_mn = p.C_img_mn ? p.C_img_mn + ((size_t)(c8 >> 4) * ((p.M + 31) >> 5) + (m0 >> 5)) * 16384 +
+                                                  ((((m0 & 31) >> 3) * 128) + (c8 & 15) * 8) * 16 + (odd ? 64 : 0) : nullptr;
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {     // row pairs (0,1) and (2,3) of this lane's four rows
           float hi8[8], lo8[8];
@@ -164,6 +167,10 @@ __global__ void __launch_bounds__(SK_THREADS) thin_smallk_kernel(GemmParams p, i
             float x[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) { x[j] = odd ? oth[i][j] : own[i][j]; x[4 + j] = odd ? own[i][j] : oth[i][j]; }
+            if (m0 + (odd ? 4 : 0) + i >= p.M) {   // in the MN-major image the rows are a reduction index: must read as zero
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = 0.f;
+            }
             uint32_t h[4], l[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) split_pack2(x[2 * j], x[2 * j + 1], h[j], l[j]);
@@ -171,8 +178,14 @@ __global__ void __launch_bounds__(SK_THREADS) thin_smallk_kernel(GemmParams p, i
             for (int j = 0; j < 4; ++j) { hi8[rr * 4 + j] = __uint_as_float(h[j]); lo8[rr * 4 + j] = __uint_as_float(l[j]); }
           }
           if (m0 + (odd ? 4 : 0) + 2 * pr < p.M) {       // rows past M only feed masked output rows of the consumer
-            st_global_v8(reinterpret_cast<float*>(base + pr * 32), hi8);
-            st_global_v8(reinterpret_cast<float*>(base + 8192 + pr * 32), lo8);
+            if (base) {
+              st_global_v8(reinterpret_cast<float*>(base + pr * 32), hi8);
+              st_global_v8(reinterpret_cast<float*>(base + 8192 + pr * 32), lo8);
+            }
+            if (base_mn) {
+              st_global_v8(reinterpret_cast<float*>(base_mn + pr * 32), hi8);
+              st_global_v8(reinterpret_cast<float*>(base_mn + 8192 + pr * 32), lo8);
+            }
           }
         }
       }
@@ -372,7 +385,7 @@ int gemm_thin_try(const GemmParams& p, GemmLayout layout, cudaStream_t stream, b
     return nn ? launch_thin_smalln<true, 32>(p, stream) : launch_thin_smalln<false, 32>(p, stream);
   }
   if (p.K + p.K2 <= SK_KMAX && (p.K2 == 0 || !nn)) {
-    R2D2_REQUIRE(!p.C_img_k || (p.N % 32 == 0), "operand image needs N % 32 == 0");
+    R2D2_REQUIRE(!(p.C_img_k || p.C_img_mn) || (p.N % 32 == 0), "operand image needs N % 32 == 0");
     *handled = true;
     const int row_tiles = ceil_div(p.M, SK_ROWS), ny = ceil_div(p.N, SK_COLS);
     int gx = 444 / ny;                                 // 3 resident blocks per SM (registers)

@@ -28,6 +28,7 @@ size_t ChainWs::floats(const NetShape& s, int T, int B, int repeat) {
     n += align64(pad_to(TB, 128) * 4 * H);
     n += align64(pad_to(S * B, 32) * 4 * H);
     if (repeat > 1) n += align64(pad_to(TB, 32) * 4 * H);
+    n += align64(pad_to(TB, 32) * pad_to(H, 128));
   }
   return n;
 }
@@ -55,6 +56,7 @@ ChainWs ChainWs::carve(float* base, const NetShape& s, int T, int B, int repeat)
     w.img_k = reinterpret_cast<unsigned char*>(take(pad_to(TB, 128) * 4 * H));
     w.img_mn_dg = reinterpret_cast<unsigned char*>(take(pad_to(S * B, 32) * 4 * H));
     w.img_mn_gin = (repeat > 1) ? reinterpret_cast<unsigned char*>(take(pad_to(TB, 32) * 4 * H)) : w.img_mn_dg;
+    w.img_z_mn = reinterpret_cast<unsigned char*>(take(pad_to(TB, 32) * pad_to(H, 128)));
   }
   return w;
 }
@@ -74,6 +76,13 @@ int net_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, const 
     // idle during the forward pass)
     z1_img = ws.img_k != nullptr && gemm_emits_operand_image(H, I);
     if (z1_img) g.C_img_k = ws.img_k;
+    if (z1_img && ws.keep_z1_image && ws.img_z_mn) {   // second copy as the B operand of dW_ih (BPTT of this chain)
+      g.C_img_mn = ws.img_z_mn;
+      if (M % 32 != 0) {   // rows of the last 32-row tile that no batch row maps to are part of a reduction: zeros
+        const size_t kt = (size_t)(M + 31) / 32;
+        R2D2_CUDA_TRY(cudaMemset2DAsync(ws.img_z_mn + (kt - 1) * 16384, kt * 16384, 0, 16384, (size_t)(H + 127) / 128, stream));
+      }
+    }
     R2D2_TRY(gemm_f32(g, GEMM_NT, stream));
   }
   R2D2_TRY(add_vec(P.bih, P.bhh, ws.bias_sum, 4 * H, stream));
@@ -158,6 +167,7 @@ int net_backward(const NetShape& s, const NetParams& P, const NetParams* G, cons
       GemmParams g;
       g.A = dgin; g.lda = 4 * H; g.B = ws.z1; g.ldb = H; g.K = M;
       if (use_img) g.A_img = ws.img_mn_gin;
+      if (use_img && ws.keep_z1_image && ws.img_z_mn && gemm_emits_operand_image(H, I)) g.B_img = ws.img_z_mn;
       g.C = G->wih; g.ldc = H; g.M = 4 * H; g.N = H; g.split_k = gemm_suggest_split_k(4 * H, H, M);
       g.reuse_packed_a = (repeat == 1);   // same dG operand as the dW_hh product just above
       R2D2_TRY(gemm_f32(g, GEMM_TN, stream));
