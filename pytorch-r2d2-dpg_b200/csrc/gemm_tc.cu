@@ -1,17 +1,20 @@
-// gemm_f32 on the 5th-gen tensor cores (sm_100a), two kernels per call:
+// gemm_f32 on the 5th-gen tensor cores (sm_100a):
 //
-//  1. pack_operand_kernel: fp32 operand (any leading dimension, ragged edges) -> bf16 hi/lo planes stored TILE-MAJOR in
-//     exactly the shared-memory image the MMA wants: one 16 KB block per (128-row tile, 32-deep k tile) = hi plane
-//     (8 KB) + lo plane (8 KB) in UMMA core-matrix order, zero padded.  HBM-bound elementwise pass (8 B/element).
-//  2. gemm_packed_kernel: per CTA one 128 x 128 output tile.  A producer thread streams the packed tiles with 1-D
-//     bulk copies (cp.async.bulk ... mbarrier::complete_tx, no tensor map, no per-element work) through a 3-stage
-//     ring; one elected thread issues tcgen05.mma (M=128, N<=128, K=16; passes lo*hi + hi*lo + hi*hi) into a TMEM
-//     accumulator; four epilogue warps read it back with tcgen05.ld and apply bias / tanh / dtanh / +Z or the
-//     split-K reduction.  96 KB smem + 128 TMEM columns per CTA -> two CTAs per SM overlap each other's epilogue.
+//  1. operand images: every operand is bf16 hi/lo planes stored TILE-MAJOR in exactly the shared-memory image the MMA
+//     wants - one 16 KB block per (128-row tile, 32-deep k tile) = hi plane (8 KB) + lo plane (8 KB) in UMMA
+//     core-matrix order, zero padded.  Producers that can write it directly do (GemmParams::A_img / B_img: the BPTT
+//     scan for dG, the l1 kernel for z1); otherwise pack_operand_kernel converts the fp32 tensor (any leading
+//     dimension, ragged edges) in an HBM-bound elementwise pass (8 B/element).
+//  2. gemm_packed_kernel<NBT>: per CTA one 128 x (128 NBT) output tile.  A producer thread streams the tile images with
+//     1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx, no tensor map, no per-element work) through a 2-3
+//     stage ring; one elected thread issues tcgen05.mma (M=128, N<=128, K=16; passes lo*hi + hi*lo + hi*hi) into one
+//     TMEM accumulator per B tile; eight epilogue warps read them back with tcgen05.ld, transpose 32 x 32 blocks
+//     through the idle stage buffers and apply bias / tanh / dtanh / +Z or the split-K reduction with line-coalesced
+//     global accesses.  <= 96 KB smem + <= 256 TMEM columns per CTA -> two CTAs per SM overlap each other's epilogue.
 //
-// Why the pre-pass: staging fp32 through shared memory inside the GEMM (cp.async -> ld.shared -> split ->
-// st.shared) cost 60% of the kernel (ablation in profiles/r01_summary.md); the packed image is the same byte
-// count as the fp32 operand and is re-read ~N/128 (A) or ~M/128 (B) times from L2.
+// Why images instead of fp32 operands: staging fp32 through shared memory inside the GEMM (cp.async -> ld.shared ->
+// split -> st.shared) cost 60% of the kernel (ablation in profiles/r01_summary.md); the image is the same byte count
+// as the fp32 operand and is re-read ~N/256 (A) or ~M/128 (B) times from L2.
 #include <stdlib.h>
 
 #include <map>

@@ -1,18 +1,21 @@
 // tcgen05 / TMEM version of the persistent cluster LSTM scan (forward + BPTT) for sm_100a.
 //
-// Same decomposition as the mma.sync kernels in lstm_scan.cu (cluster of C = H/32 CTAs per NB batch rows,
+// Same decomposition as the mma.sync kernels in lstm_scan.cu (cluster of C = H/32 CTAs per <= 32 batch rows,
 // CTA `rank` owns hidden units [32 rank, 32 rank + 32) = 128 gate rows of W_hh), but
-//   * the W_hh slice lives in SHARED memory as bf16 hi/lo planes in the UMMA K-major core-matrix layout and
-//     is read directly by the 5th-gen tensor cores: per cell step one elected thread issues
-//     (H/16) x 3 tcgen05.mma (M=128 gate rows, N=NB batch columns, K=16; passes lo*hi, hi*lo, hi*hi) that
-//     accumulate in TMEM; tcgen05.commit -> mbarrier tells the epilogue warps;
-//   * the epilogue reads the accumulator with tcgen05.ld (lane = gate row), finishes the LSTM cell in
-//     registers and stages h_t (bf16 hi/lo, already in the operand layout of the next step);
-//   * the h_t all-gather inside the cluster is 2*C bulk shared->remote-shared copies
-//     (cp.async.bulk.shared::cluster) that complete transaction bytes on the DESTINATION's mbarrier: no
-//     cluster-wide barrier and no memory fence on the global stores of gates / h / c on the serial chain
-//     (the v1 kernel spent 24% of its samples in the barrier's release fence, profiles/r01_*).
-// Backward: P[H x NB] = W_slice^T [H x 128] * dG^T via tcgen05, fp32 partial sums reduce-scattered with bulk copies.
+//   * the W_hh slice is written ONCE into tensor memory (bf16 hi/lo planes, tcgen05.st) and stays there as the A
+//     operand of every step; per cell step one elected thread issues (H/16) x 3 tcgen05.mma (M=128 gate rows,
+//     N = 16 | 32 batch columns, K=16; passes lo*hi, hi*lo, hi*hi; B = the h tile in shared memory) that accumulate in
+//     TMEM; tcgen05.commit -> mbarrier tells the cell warps;
+//   * the cell warps read the accumulator with tcgen05.ld (lane = gate row), transpose it through shared memory,
+//     finish the LSTM cell in registers and stage h_t (bf16 hi/lo, already in the operand layout of the next step);
+//   * the h_t all-gather inside the cluster is bulk shared->remote-shared copies (cp.async.bulk.shared::cluster)
+//     that complete transaction bytes on the DESTINATION's mbarrier: no cluster-wide barrier and no memory fence
+//     on the global stores of gates / h / c on the serial chain (the v1 kernel spent 24% of its samples in the
+//     barrier's release fence, profiles/r01_*);
+//   * lstm_scan_fwd_pp_kernel (clusters with 17..32 rows, the cfg-2 case) alternates two <= 16-row sub-tiles through
+//     this pipeline with a dedicated MMA warp.
+// Backward: P[H x NB] = W_slice^T [H x 128] * dG^T via tcgen05 (W^T tiles in TMEM), fp32 partial sums reduce-scattered
+// with bulk copies; dG also leaves as the packed operand images of the GEMMs that consume it, bias sums fused.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
