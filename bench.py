@@ -175,11 +175,13 @@ def run_reference(args, c):
         return
     value, sec, threads, done = time_cpu_port(c, args.steps, args.warmup, budget_s=240.0)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "seq-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "steps": args.steps, "steps_timed": done, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: " + " ".join(f"{k}={v}" for k, v in c.items()),
                        "note": "reference CPU learner (oracle/ref_port.py port; /root/reference is python and not "
-                               "present on this box), full batch per step"},
+                               "present on this box), full batch per step; a step is one full learner iteration "
+                               "(~1-2 s on the host): at most 240 s of them are timed (steps_timed), the rate does "
+                               "not depend on the count"},
             "cpu_baseline": {"value": value, "unit": "seq-steps/s", "cores": threads, "kind": "port",
                              "sample": f"{done} full learner iterations at batch {c['batch']} after {args.warmup} warm-up, "
                                        f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)"},
