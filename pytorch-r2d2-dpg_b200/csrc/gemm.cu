@@ -2,6 +2,7 @@
 // tensor-core MMAs (3 passes: hi*hi + lo*hi + hi*lo) with fp32 accumulation.
 // CTA tile 128x64x32, 8 warps (4 along M x 2 along N), register-staged double buffering.
 #include "gemm.cuh"
+#include "elementwise.cuh"
 
 #include <stdlib.h>
 
@@ -256,6 +257,11 @@ static int g_skinny_mma = 1;
 void gemm_set_impl_skinny_mma(int on) { g_skinny_mma = on ? 1 : 0; }
 int gemm_get_impl_skinny_mma() { return g_skinny_mma; }
 
+bool gemm_supports_bias2(int M, int N, int K) {
+  const bool skinny = (K < 64) || (N < 32) || (M < 32);
+  return gemm_get_impl() == 1 && !(skinny && gemm_get_impl_skinny_mma());
+}
+
 bool gemm_emits_operand_image(int N, int K_total) {
   return gemm_get_impl() == 1 && gemm_get_impl_skinny_mma() && K_total <= 32 && N > 32 && N % 32 == 0;
 }
@@ -274,7 +280,20 @@ int gemm_suggest_split_k(int M, int N, int K) {
   return s;
 }
 
+static int gemm_f32_dispatch(const GemmParams& p, GemmLayout layout, cudaStream_t stream, bool* colsums_done);
+
 int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
+  R2D2_REQUIRE((!p.colsum_a && !p.colsum_b) || layout == GEMM_TN, "column sums ride on TN products only");
+  bool colsums_done = false;
+  R2D2_TRY(gemm_f32_dispatch(p, layout, stream, &colsums_done));
+  if (!colsums_done) {   // the kernel that took the product does not fuse them
+    if (p.colsum_a) R2D2_TRY(colsum(p.A, p.lda, p.K, p.M, p.colsum_a, nullptr, stream));
+    if (p.colsum_b) R2D2_TRY(colsum(p.B, p.ldb, p.K, p.N, p.colsum_b, nullptr, stream));
+  }
+  return R2D2_OK;
+}
+
+static int gemm_f32_dispatch(const GemmParams& p, GemmLayout layout, cudaStream_t stream, bool* colsums_done) {
   R2D2_REQUIRE((p.A || p.A_img) && (p.B || p.B_img) && p.C, "null operand");
   if (p.A_img || p.B_img) {
     R2D2_REQUIRE(p.K2 == 0, "packed A with a second K segment");
@@ -293,8 +312,9 @@ int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   if (gemm_get_impl() == 1 && gemm_get_impl_skinny_mma()) {   // default mode: degenerate shapes -> fp32 streaming kernels
     bool handled = false;
     R2D2_TRY(gemm_thin_try(p, layout, stream, &handled));
-    if (handled) return R2D2_OK;
+    if (handled) { *colsums_done = true; return R2D2_OK; }
   }
+  R2D2_REQUIRE(!p.bias2 || gemm_supports_bias2(p.M, p.N, p.K + p.K2), "bias2 needs the tcgen05 path (gemm_supports_bias2)");
   R2D2_REQUIRE(!p.C_img_k && !p.C_img_mn, "C_img_* is only produced by the small-K streaming kernel (see gemm_emits_operand_image)");
   if (gemm_get_impl() == 1 && !(skinny && gemm_get_impl_skinny_mma())) {
     static int dbg = -1;

@@ -29,6 +29,8 @@ struct GemmParams {
   float* C = nullptr;        long long ldc = 0;
   int M = 0, N = 0, K = 0;
   const float* bias = nullptr;          // [N]
+  const float* bias2 = nullptr;         // [N] second bias added to the first (b_ih + b_hh); tcgen05 path only, see
+                                        // gemm_supports_bias2
   const float* Z = nullptr;  long long ldz = 0;   // [M,N] aux for the epilogue
   int epilogue = EPI_NONE;
   int split_k = 1;           // >1: partial products are atomically added into C (C must be pre-zeroed)
@@ -39,6 +41,8 @@ struct GemmParams {
   unsigned char* C_img_mn = nullptr;     // same, MN-major image [ceil(N/128)][ceil(M/32)][16 KB]: C as the B operand of a TN
                              // product that contracts over C's rows (z1 in dW_ih)
   const unsigned char* B_img = nullptr;   // tcgen05 path: B already packed (image of this call's layout and tiling)
+  float* colsum_a = nullptr;             // TN only: also ADD the column sums of A[K,M] (M values) / B[K,N] (N values) here:
+  float* colsum_b = nullptr;             // the bias gradient that goes with a weight gradient reads the same rows
   int reuse_packed_a = 0;    // tcgen05 path: A (pointer, shape, layout) is the operand the previous gemm_f32 call packed
                              // and its contents have not changed since -> skip the pack pass (dW_hh then dW_ih of a chain)
   int debug_flags = 0;       // dev only (env R2D2_GEMM_DEBUG): 1 = producers skip fetch+convert, 2 = skip MMAs, 4 = skip epilogue stores
@@ -47,6 +51,8 @@ struct GemmParams {
 int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream);
 // true when gemm_f32 will honour GemmParams::C_img_k for an NT product with these sizes (small-K streaming kernel selected)
 bool gemm_emits_operand_image(int N, int K_total);
+// true when gemm_f32 will take this NT product on the tcgen05 path, which honours GemmParams::bias2
+bool gemm_supports_bias2(int M, int N, int K);
 // picks a split-K factor so that a skinny-output wgrad GEMM fills the 148 SMs
 int gemm_suggest_split_k(int M, int N, int K);
 

@@ -93,6 +93,7 @@ struct PackedGemmParams {
   float* C; long long ldc;
   int M, N;
   const float* bias;
+  const float* bias2;
   const float* Z; long long ldz;
   int epilogue, split_k;
   int a_mn, b_mn;            // operand majors (1 = MN-major)
@@ -233,6 +234,10 @@ __global__ void __launch_bounds__(PACKED_GEMM_THREADS, 2) gemm_packed_kernel(Pac
 #pragma unroll
           for (int j = 0; j < 4; ++j) if (j < nv) bv[j] = __ldg(p.bias + col + j);
         }
+        if (p.bias2) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nv) bv[j] += __ldg(p.bias2 + col + j);
+        }
       }
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -360,7 +365,7 @@ int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   }
   PackedGemmParams q;
   q.pa = p.A_img ? p.A_img : g_pack_a.ptr; q.pb = p.B_img ? p.B_img : g_pack_b.ptr; q.k_tiles = k_tiles; q.C = p.C; q.ldc = p.ldc; q.M = p.M; q.N = p.N;
-  q.bias = p.bias; q.Z = p.Z; q.ldz = p.ldz; q.epilogue = p.epilogue; q.split_k = p.split_k;
+  q.bias = p.bias; q.bias2 = p.bias ? p.bias2 : nullptr; q.Z = p.Z; q.ldz = p.ldz; q.epilogue = p.epilogue; q.split_k = p.split_k;
   q.a_mn = a_mn; q.b_mn = b_mn; q.debug_flags = p.debug_flags;
   static int force_nbt = -1;
   if (force_nbt < 0) { const char* e = getenv("R2D2_GEMM_NBT"); force_nbt = e ? atoi(e) : 0; }

@@ -270,7 +270,8 @@ constexpr int TN_THREADS = 256, TN_CHUNK = 32, TN_BATCH = 16;
 template <int QP>
 __global__ void __launch_bounds__(TN_THREADS) thin_tn_kernel(const float* __restrict__ X, long long ldx, int P,
                                                              const float* __restrict__ Y, long long ldy, int Q, int K,
-                                                             float* __restrict__ C, long long ldc, int small_is_m) {
+                                                             float* __restrict__ C, long long ldc, int small_is_m,
+                                                             float* __restrict__ colsum_x, float* __restrict__ colsum_y) {
   __shared__ __align__(16) float Ys[TN_CHUNK][QP];
   __shared__ float Out[TN_THREADS][QP + 1];
   const int tid = threadIdx.x;
@@ -280,6 +281,8 @@ __global__ void __launch_bounds__(TN_THREADS) thin_tn_kernel(const float* __rest
   float acc[QP];
 #pragma unroll
   for (int q = 0; q < QP; ++q) acc[q] = 0.f;
+  float xsum = 0.f, ysum = 0.f;   // optional column sums of the two operands (bias gradients), each element counted once
+  const bool do_ysum = colsum_y != nullptr && blockIdx.y == 0 && tid < Q;
   const int chunks = (K + TN_CHUNK - 1) / TN_CHUNK;
   for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
     const int r0 = ch * TN_CHUNK;
@@ -290,6 +293,10 @@ __global__ void __launch_bounds__(TN_THREADS) thin_tn_kernel(const float* __rest
       Ys[r][q] = (r < nr && q < Q) ? __ldg(Y + (long long)(r0 + r) * ldy + q) : 0.f;
     }
     __syncthreads();
+    if (do_ysum) {
+#pragma unroll 8
+      for (int r = 0; r < TN_CHUNK; ++r) ysum += Ys[r][tid];   // rows >= nr hold zeros
+    }
     const float* xp = X + (long long)r0 * ldx + pc;
     for (int rb = 0; rb < nr; rb += TN_BATCH) {
       float x[TN_BATCH];
@@ -297,6 +304,7 @@ __global__ void __launch_bounds__(TN_THREADS) thin_tn_kernel(const float* __rest
       for (int i = 0; i < TN_BATCH; ++i) x[i] = (pon && rb + i < nr) ? __ldg(xp + (long long)(rb + i) * ldx) : 0.f;
 #pragma unroll
       for (int i = 0; i < TN_BATCH; ++i) {
+        xsum += x[i];
 #pragma unroll
         for (int q4 = 0; q4 < QP / 4; ++q4) {
           const float4 y = *reinterpret_cast<const float4*>(&Ys[rb + i][q4 * 4]);   // rows >= nr hold zeros
@@ -306,6 +314,8 @@ __global__ void __launch_bounds__(TN_THREADS) thin_tn_kernel(const float* __rest
       }
     }
   }
+  if (colsum_x && pon) atomicAdd(colsum_x + pc, xsum);
+  if (do_ysum) atomicAdd(colsum_y + tid, ysum);
 #pragma unroll
   for (int q = 0; q < QP; ++q) Out[tid][q] = acc[q];
   __syncthreads();
@@ -329,13 +339,13 @@ bool aligned16(const float* ptr, long long ld) {
 
 template <int QP>
 int launch_thin_tn(const float* X, long long ldx, int P, const float* Y, long long ldy, int Q, int K, float* C,
-                   long long ldc, int small_is_m, cudaStream_t stream) {
+                   long long ldc, int small_is_m, float* colsum_x, float* colsum_y, cudaStream_t stream) {
   const int chunks = ceil_div(K, TN_CHUNK), py = ceil_div(P, TN_THREADS);
   int gx = 888 / py;                                   // ~6 resident blocks per SM
   if (gx < 1) gx = 1;
   if (gx > chunks) gx = chunks;
   gx = ceil_div(chunks, ceil_div(chunks, gx));         // equal number of chunks per block
-  thin_tn_kernel<QP><<<dim3(gx, py), TN_THREADS, 0, stream>>>(X, ldx, P, Y, ldy, Q, K, C, ldc, small_is_m);
+  thin_tn_kernel<QP><<<dim3(gx, py), TN_THREADS, 0, stream>>>(X, ldx, P, Y, ldy, Q, K, C, ldc, small_is_m, colsum_x, colsum_y);
   count_launch();
   R2D2_CUDA_TRY(cudaGetLastError());
   return R2D2_OK;
@@ -370,11 +380,13 @@ int gemm_thin_try(const GemmParams& p, GemmLayout layout, cudaStream_t stream, b
     const float* X = small_is_m ? p.B : p.A;  const long long ldx = small_is_m ? p.ldb : p.lda;
     const float* Y = small_is_m ? p.A : p.B;  const long long ldy = small_is_m ? p.lda : p.ldb;
     const int P = small_is_m ? p.N : p.M, Q = small_is_m ? p.M : p.N;
+    float* csx = small_is_m ? p.colsum_b : p.colsum_a;
+    float* csy = small_is_m ? p.colsum_a : p.colsum_b;
     *handled = true;
-    if (Q <= 8)  return launch_thin_tn<8>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, stream);
-    if (Q <= 16) return launch_thin_tn<16>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, stream);
-    if (Q <= 24) return launch_thin_tn<24>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, stream);
-    return launch_thin_tn<32>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, stream);
+    if (Q <= 8)  return launch_thin_tn<8>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, csx, csy, stream);
+    if (Q <= 16) return launch_thin_tn<16>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, csx, csy, stream);
+    if (Q <= 24) return launch_thin_tn<24>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, csx, csy, stream);
+    return launch_thin_tn<32>(X, ldx, P, Y, ldy, Q, p.K, p.C, p.ldc, small_is_m ? 1 : 0, csx, csy, stream);
   }
   if (p.split_k != 1) return R2D2_OK;
   const bool nn = layout == GEMM_NN;

@@ -85,11 +85,13 @@ int net_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, const 
     }
     R2D2_TRY(gemm_f32(g, GEMM_NT, stream));
   }
-  R2D2_TRY(add_vec(P.bih, P.bhh, ws.bias_sum, 4 * H, stream));
+  const bool two_bias = gemm_supports_bias2(M, 4 * H, H);   // the tcgen05 epilogue adds both biases itself
+  if (!two_bias) R2D2_TRY(add_vec(P.bih, P.bhh, ws.bias_sum, 4 * H, stream));
   {  // gin = z1 * W_ih^T + (b_ih + b_hh)   (input half of LSTMCell, models.py:37,80) for all rows at once
     GemmParams g;
     g.A = ws.z1; g.lda = H; g.B = P.wih; g.ldb = H; g.K = H;
-    g.C = ws.gin; g.ldc = 4 * H; g.M = M; g.N = 4 * H; g.bias = ws.bias_sum;
+    g.C = ws.gin; g.ldc = 4 * H; g.M = M; g.N = 4 * H;
+    if (two_bias) { g.bias = P.bih; g.bias2 = P.bhh; } else g.bias = ws.bias_sum;
     if (z1_img) g.A_img = ws.img_k;
     R2D2_TRY(gemm_f32(g, GEMM_NT, stream));
   }
@@ -129,8 +131,8 @@ int net_backward(const NetShape& s, const NetParams& P, const NetParams* G, cons
     GemmParams g;
     g.A = d_pre; g.lda = A; g.B = hin; g.ldb = H; g.K = Mh;
     g.C = G->w3; g.ldc = H; g.M = A; g.N = H; g.split_k = gemm_suggest_split_k(A, H, Mh);
+    g.colsum_a = G->b3;   // db3 = column sums of d_pre: same rows, same pass
     R2D2_TRY(gemm_f32(g, GEMM_TN, stream));
-    R2D2_TRY(colsum(d_pre, A, Mh, A, G->b3, nullptr, stream));
   }
   {  // dL/dh from the head: d_pre * W3 (actor: through tanh(h), models.py:38)
     GemmParams g;
@@ -184,13 +186,14 @@ int net_backward(const NetShape& s, const NetParams& P, const NetParams* G, cons
     GemmParams g;
     g.A = ws.z1; g.lda = H; g.B = obs; g.ldb = O; g.K = M;
     g.C = G->w1; g.ldc = I; g.M = H; g.N = O; g.split_k = gemm_suggest_split_k(H, O, M);
+    g.colsum_a = G->b1;   // db1 = column sums of d(pre-l1)
     R2D2_TRY(gemm_f32(g, GEMM_TN, stream));
     if (s.critic) {
       GemmParams g2 = g;
+      g2.colsum_a = nullptr;
       g2.B = act; g2.ldb = A; g2.C = G->w1 + O; g2.N = A; g2.split_k = gemm_suggest_split_k(H, A, M);
       R2D2_TRY(gemm_f32(g2, GEMM_TN, stream));
     }
-    R2D2_TRY(colsum(ws.z1, H, M, H, G->b1, nullptr, stream));
   }
   if (d_act) {  // gradient wrt the action half of the critic input (DPG path, learner.py:123-127)
     R2D2_REQUIRE(s.critic, "d_act only for the critic");
