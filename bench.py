@@ -304,23 +304,47 @@ def main():
     h2d = sum(v.numel() * 4 for v in pool[0].values())
     d2h = (B + 2) * 4
 
+    # Double-buffered feed: the pinned batch of step i+1 crosses PCIe on a copy stream while step i computes; the
+    # compute stream only does a device-to-device move of the staged batch (5 MB at HBM speed) before each step.
+    keys = list(pool[0].keys())
+    copy_stream = torch.cuda.Stream()
+    stage = [{k: torch.empty_like(getattr(eng, k)) for k in keys} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    for e in consumed:
+        e.record(torch.cuda.current_stream())
+
+    def prefetch(i):
+        s_ = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s_])          # the staged batch of step i-2 has been moved out
+            for k, v in pool[i % n_pool].items():
+                stage[s_][k].copy_(v, non_blocking=True)
+            ready[s_].record(copy_stream)
+
     def step_host(i):
-        hb = pool[i % n_pool]
-        for k, v in hb.items():
-            getattr(eng, k).copy_(v, non_blocking=True)
+        s_ = i % 2
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[s_])
+        for k in keys:
+            getattr(eng, k).copy_(stage[s_][k], non_blocking=True)
+        consumed[s_].record(cur)
+        prefetch(i + 1)                                   # H2D of the next step's inputs, overlapped with this step
         eng.step()
         host_prio.copy_(eng.priority, non_blocking=True)
         host_loss.copy_(eng.losses, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the host consumes the priorities every iteration
+        cur.synchronize()                                 # the host consumes the priorities every iteration
 
+    prefetch(0)
     for i in range(args.warmup):
         step_host(i)
     barrier()
     ev0.record()
-    for i in range(args.steps):
+    for i in range(args.warmup, args.warmup + args.steps):
         step_host(i)
     ev1.record()
     barrier()
+    copy_stream.synchronize()
     ms_e2e = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
     if dist is not None:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
@@ -386,7 +410,9 @@ def main():
                            "replay_shard": f"{args.episodes} episodes x {ep_len + cfg.n_step} rows per GPU in HBM",
                            "l2": "inputs larger than L2: every step streams >1 GB of activations and gathers its batch "
                                  "from a multi-GB replay shard"},
-                "e2e": {"value": e2e_value, "unit": "seq-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": "seq-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "feed": "pinned host batch -> staging buffer on a copy stream (step i+1 overlaps step i), "
+                                "priorities + losses read back and the stream synchronised every step"},
                 "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "clocks": clk}
         emit(line)
