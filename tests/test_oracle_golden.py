@@ -90,3 +90,36 @@ def test_known_answers():
     assert list(k["slice_b4"]) == [3, 3, 3, 2]          # learner.py:137 drops the last step of b = B-1
     for row, want in zip(k["prio_in"], k["prio_out"]):
         assert abs(ref_port.sequence_priority(row) - want) < 1e-6
+
+
+EDGE_CASES = [
+    # obs, act, hidden, batch, burn_in, learning, n_step  - shapes the goldens do not reach
+    (3, 1, 32, 1, 1, 2, 1),      # single sequence, single action, n_step 1: the [b:-1:B] slice drops the ONLY last row
+    (5, 2, 32, 3, 1, 3, 2),      # shortest burn-in the reference supports (learner.py:93-95 needs >= 1 row)
+    (4, 3, 64, 5, 2, 6, 4),      # n_step close to the learning length
+    (6, 2, 96, 2, 3, 4, 5),      # hidden size outside the cluster kernels (generic scan path on the GPU)
+]
+
+
+@pytest.mark.parametrize("obs,act,hidden,batch,burn_in,learning,n_step", EDGE_CASES)
+def test_numpy_oracle_matches_port_on_edge_shapes(obs, act, hidden, batch, burn_in, learning, n_step):
+    """The float64 manual-BPTT restatement (the per-kernel parity target of the CUDA tests) against the torch port
+    (autograd, pinned to the unmodified reference by the tests above) where the reference goldens have no fixture:
+    B = 1, A = 1, n_step = 1, minimal burn-in, odd hidden sizes.  Two consecutive iterations (Adam state carried)."""
+    torch.set_num_threads(1)
+    pc = ref_port.PathConfig(obs=obs, act=act, hidden=hidden, batch=batch, burn_in=burn_in, learning=learning, n_step=n_step)
+    port = ref_port.PortLearner(pc, seed=11)
+    sd = lambda m: {k: v.detach().numpy().copy() for k, v in m.state_dict().items()}  # noqa: E731
+    ol = lo.OracleLearner(sd(port.actor), sd(port.critic), burn_in=burn_in, learning=learning, n_step=n_step)
+    for it in range(2):
+        batch_np = ref_port.synthetic_batch(pc, seed=100 + it)
+        ref = port.iteration(batch_np)
+        out = ol.iteration(batch_np)
+        assert rel_l2(out["q_value"], ref["q_value"]) < 5e-5
+        assert rel_l2(out["target_q_value"], ref["target_q_value"]) < 5e-5
+        assert rel_l2(out["priority"], ref["priority"]) < 5e-5
+        assert abs(out["critic_loss"] - ref["critic_loss"]) < 1e-4 * abs(ref["critic_loss"]) + 1e-9
+        assert abs(out["actor_loss"] - ref["actor_loss"]) < 1e-4 * abs(ref["actor_loss"]) + 1e-9
+        for net in ("actor", "critic"):
+            for k in lo.PARAM_KEYS:
+                assert rel_l2(out[f"{net}_grad"][k], ref[f"{net}_grad"][k]) < 5e-4, (it, net, k)
