@@ -171,3 +171,41 @@ def test_replay_to_learner_roundtrip(eng_mod):
     for l, p in last.items():
         assert leaves[l].item() == np.float32(p)
     assert np.isfinite(pr).all() and (pr >= 0).all()
+
+
+EDGE_CASES = [
+    # obs, act, hidden, batch, burn_in, learning, n_step  (same list as tests/test_oracle_golden.py)
+    (3, 1, 32, 1, 1, 2, 1),
+    (5, 2, 32, 3, 1, 3, 2),
+    (4, 3, 64, 5, 2, 6, 4),
+    (6, 2, 96, 2, 3, 4, 5),
+]
+
+
+@pytest.mark.parametrize("obs,act,hidden,batch,burn_in,learning,n_step", EDGE_CASES)
+def test_edge_shapes_against_port(eng_mod, obs, act, hidden, batch, burn_in, learning, n_step):
+    """B = 1, A = 1, n_step = 1, minimal burn-in, a hidden size on the generic scan path: two consecutive iterations
+    against the CPU port (which tests/test_oracle_golden.py pins to the unmodified reference)."""
+    pc = ref_port.PathConfig(obs=obs, act=act, hidden=hidden, batch=batch, burn_in=burn_in, learning=learning, n_step=n_step)
+    torch.set_num_threads(1)
+    port = ref_port.PortLearner(pc, seed=11)
+    cfg = eng_mod.PathConfig(obs=obs, act=act, hidden=hidden, batch=batch, burn_in=burn_in, learning=learning, n_step=n_step)
+    eng = eng_mod.LearnerEngine(cfg)
+    sd = lambda m: {k: v.detach().numpy() for k, v in m.state_dict().items()}  # noqa: E731
+    eng.load_state_dicts(sd(port.actor), sd(port.critic))
+    for it in range(2):
+        batch_np = ref_port.synthetic_batch(pc, seed=100 + it)
+        ref = port.iteration(batch_np)
+        eng.set_batch(batch_np)
+        eng.step()
+        torch.cuda.synchronize()
+        errs = {"q": rel_l2(eng.q_value.cpu().numpy(), ref["q_value"]),
+                "target": rel_l2(eng.target_q_value.cpu().numpy(), ref["target_q_value"]),
+                "prio": rel_l2(eng.priority.cpu().numpy(), ref["priority"])}
+        for net in ("actor", "critic"):
+            gr, pa = flat_sd(eng.views(net, "grads")), flat_sd(eng.views(net))
+            for k in eng_mod.PARAM_KEYS:
+                errs[f"{net}_grad/{k}"] = rel_l2(gr[k], ref[f"{net}_grad"][k])
+                errs[f"{net}_after/{k}"] = rel_l2(pa[k], ref[f"{net}_after"][k])
+        bad = {k: v for k, v in errs.items() if not v < TOL}
+        assert not bad, f"iteration {it}: {bad}"
