@@ -118,6 +118,18 @@ def log(msg):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
+def cpu_model():
+    """CPU model string of the host the CPU baseline ran on (SURVEY 8d asks for it next to os.cpu_count())."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def pick_cpu_threads(c):
     """torch CPU ops of this size (batch x hidden LSTMCell steps) stop scaling - and can collapse - long
     before a 100+ core box is full, so probe a few thread counts on a short LSTMCell fwd+bwd loop and keep
@@ -184,7 +196,8 @@ def run_reference(args, c):
                                "not depend on the count"},
             "cpu_baseline": {"value": value, "unit": "seq-steps/s", "cores": threads, "kind": "port",
                              "sample": f"{done} full learner iterations at batch {c['batch']} after {args.warmup} warm-up, "
-                                       f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)"},
+                                       f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)",
+                             "cpu_model": cpu_model(), "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": "seq-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -400,7 +413,8 @@ def main():
         v, sec, threads, done = time_cpu_port(c, args.cpu_steps, 1, budget_s=60.0)
         cpu_baseline = {"value": v, "unit": "seq-steps/s", "cores": threads, "kind": "port",
                         "sample": f"{done} full learner iterations at batch {B} after 1 warm-up ({sec:.2f} s each), "
-                                  f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)"}
+                                  f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)",
+                        "cpu_model": cpu_model(), "host_cores": os.cpu_count()}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "seq-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -413,6 +427,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "seq-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "feed": "pinned host batch -> staging buffer on a copy stream (step i+1 overlaps step i), "
                                 "priorities + losses read back and the stream synchronised every step"},
+                "iterations_per_s": world * 1e3 / ms, "rows_per_s": world * B * (cfg.burn_in + L) / (ms * 1e-3),
                 "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "clocks": clk}
         emit(line)
