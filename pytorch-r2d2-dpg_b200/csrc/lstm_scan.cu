@@ -527,7 +527,10 @@ int bwd_dispatch(const ScanBwdParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-bool lstm_scan_cluster_supported(int H) { return H == 32 || H == 64 || H == 128 || H == 256; }
+// v1 (mma.sync) cluster kernels: weights as register fragments, up to 256 hidden units
+static bool v1_cluster_supported(int H) { return H == 32 || H == 64 || H == 128 || H == 256; }
+// tcgen05 kernels: up to 512 hidden units (cluster of 16 CTAs, W_hh lo plane partly in shared memory)
+bool lstm_scan_cluster_supported(int H) { return v1_cluster_supported(H) || H == 512; }
 bool lstm_scan_backward_emits_images(int H) { return lstm_scan_cluster_supported(H) && lstm_scan_get_impl() == 1; }
 
 static int g_scan_impl = -1;
@@ -540,11 +543,11 @@ int lstm_scan_get_impl() {
   return g_scan_impl;
 }
 
-size_t lstm_scan_fwd_scratch_floats(int B, int H) {
-  return lstm_scan_cluster_supported(H) ? 0 : (size_t)B * 4 * H;
+size_t lstm_scan_fwd_scratch_floats(int B, int H) {   // the per-step path is the A/B fallback wherever v1 has no kernel
+  return v1_cluster_supported(H) ? 0 : (size_t)B * 4 * H;
 }
 size_t lstm_scan_bwd_scratch_floats(int B, int H) {
-  return lstm_scan_cluster_supported(H) ? 0 : (size_t)2 * B * H;
+  return v1_cluster_supported(H) ? 0 : (size_t)2 * B * H;
 }
 
 int lstm_scan_forward(const ScanFwdParams& p, cudaStream_t stream) {

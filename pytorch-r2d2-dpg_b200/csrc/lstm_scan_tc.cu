@@ -73,14 +73,23 @@ struct TcFwdSmem {
   static constexpr int BUF_BYTES = RG * RG_BYTES;    // = NB * H * 4
   static constexpr int OFF_HB = 0;
   static constexpr int NACC = (H / 16) < R2D2_SCAN_NACC ? (H / 16) : R2D2_SCAN_NACC;
-  // tensor memory columns: NACC independent accumulators D_a at [a*NB, ..), then the W_hh slice: hi plane at 128
-  // (H/2 columns: two bf16 per column), lo plane after it
-  static constexpr int TM_A_HI = 128, TM_A_LO = 128 + H / 2, TM_COLS = 512;
+  // tensor memory columns: NACC independent accumulators D_a at [a*NB, ..), then the W_hh slice: hi plane at TM_A_HI
+  // (H/2 columns: two bf16 per column), lo plane after it.  H = 512 (BIG): hi + lo of a 128 x 512 slice are the whole
+  // 512 columns, so the accumulators get 64 columns, the lo plane keeps its first KS_TM_LO k-steps in tensor memory
+  // and the last KS_TAIL k-steps live in shared memory (SS-mode MMAs: same instruction, A through a descriptor)
+  static constexpr bool BIG = H > 256;
+  static constexpr int TM_A_HI = BIG ? 64 : 128, TM_A_LO = TM_A_HI + H / 2, TM_COLS = 512;
+  static constexpr int KS_TM_LO = BIG ? (TM_COLS - TM_A_LO) / 8 : H / 16, KS_TAIL = H / 16 - KS_TM_LO;
+  static_assert(NACC * NB <= TM_A_HI, "accumulators overlap the weight slice in tensor memory");
   static constexpr int OFF_GT = OFF_HB + 2 * BUF_BYTES;            // fp32 [NB][GT_LD]
   static constexpr int OFF_HSTAGE = OFF_GT + NB * GT_LD * 4;       // [dbuf][row group][plane][4 chunks][8][16 B]
   static constexpr int OFF_BAR = OFF_HSTAGE + 2 * RG * SLICE;      // 3 mbarriers + tmem slot + dead flag
-  static constexpr int BYTES = OFF_BAR + 64;
+  // lo-plane tail of W_hh: per k-step one 4 KB K-major block [2 k-chunks][16 row groups][8 rows][16 B]
+  // (descriptor LBO = 2048, SBO = 128)
+  static constexpr int OFF_WTAIL = OFF_BAR + 128;
+  static constexpr int BYTES = OFF_WTAIL + KS_TAIL * 4096;
   static_assert(BYTES <= 232448, "forward scan tile does not fit in 227 KB of shared memory");
+  static_assert(OFF_WTAIL % 128 == 0, "descriptor alignment");
 };
 
 template <int H, int NB>
@@ -162,10 +171,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
         split_pack2(v.z, v.w, hi[2 * i + 1], lo[2 * i + 1]);
       }
       tc::tmem_st_32x32b_x8(lane_base + SM::TM_A_HI + ks * 8, hi);
-      tc::tmem_st_32x32b_x8(lane_base + SM::TM_A_LO + ks * 8, lo);
+      if (ks < SM::KS_TM_LO) {
+        tc::tmem_st_32x32b_x8(lane_base + SM::TM_A_LO + ks * 8, lo);
+      } else {   // lo-plane tail -> shared memory, K-major core matrices: row = local gate row q*32 + lane
+        unsigned char* d = smem + SM::OFF_WTAIL + (ks - SM::KS_TM_LO) * 4096 + (q * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(d + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
     }
     tc::tmem_wait_st();
   }
+  tc::fence_proxy_async_smem();
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
@@ -175,6 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
   const uint32_t hb_addr = tc::smem_u32(hb);
   // the operand descriptor is loop invariant up to its 16-byte start-address field: build once, add offsets per k-step
   const uint64_t db_hi0 = tc::make_smem_desc(hb_addr, 128, SM::RG_BYTES);   // buffer 0, slice 0, plane hi
+  const uint64_t wtail_desc0 = tc::make_smem_desc(tc::smem_u32(smem + SM::OFF_WTAIL), 2048, 128);
   const size_t gstride = (size_t)4 * H;
   const uint32_t step_tx = (uint32_t)(C * n_rg_valid * SM::SLICE);
 
@@ -208,7 +225,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
         const uint64_t db_hi = db_cur + (uint64_t)(((ks >> 1) * SM::SLICE + (ks & 1) * 256) >> 4);
         const uint64_t db_lo = db_hi + (uint64_t)(512 >> 4);
         const uint32_t d = tmem_base + (ks % SM::NACC) * NB;
-        tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks >= SM::NACC);
+        if (ks < SM::KS_TM_LO) tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks >= SM::NACC);
+        else tc::mma_bf16_ss(d, wtail_desc0 + (uint64_t)(((ks - SM::KS_TM_LO) * 4096) >> 4), db_hi, idesc, ks >= SM::NACC);
         tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
         tc::mma_bf16_ts(d, ta_hi, db_hi, idesc, true);
       }
@@ -272,10 +290,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_fwd_tc_kernel(ScanFwd
         tc::fence_proxy_async_smem();
         asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");   // the 8 warps that own this row group
         if (s + 1 < S && r8 < C && tc::elect_one()) {
-          const uint32_t d = r8;
           const uint32_t dst_local = hb_addr + nxt * SM::BUF_BYTES + e * SM::RG_BYTES + rank * SM::SLICE;
-          tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf + e * SM::SLICE), SM::SLICE,
-                                   tc::mapa(tc::smem_u32(&h_full[nxt]), d));
+#pragma unroll
+          for (uint32_t d = r8; d < (uint32_t)C; d += 8)   // 8 warps per row group: one (C <= 8) or two (C = 16) destinations each
+            tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), tc::smem_u32(hs_buf + e * SM::SLICE), SM::SLICE,
+                                     tc::mapa(tc::smem_u32(&h_full[nxt]), d));
         }
         if (on) {   // saved activations leave after the exchange has been started: off the serial chain
           float* go = p.gates + ((size_t)s * B + b) * gstride + ug;
@@ -579,14 +598,27 @@ struct TcBwdSmem {
   // tensor memory: NACC independent accumulators per M tile, D_(mt,a) at [(mt*NACC + a)*NB, ..); W^T tiles from
   // column 256: (mt, plane) -> 256 + (2 mt + plane) * 64
   static constexpr int NACC = R2D2_SCAN_NACC;
-  static constexpr int TM_A = 256, TM_COLS = 512;
-  static_assert(MT * NACC * NB <= 256, "accumulators overlap the weight tiles in tensor memory");
+  // H = 512 (BIG): four 128-unit tiles of W^T (hi + lo = 512 columns) do not leave room for the accumulators:
+  // accumulators [0, 128), hi tiles [128, 384), lo tiles 0 and 1 [384, 512), lo tiles 2 and 3 in SHARED memory (SS-mode
+  // MMAs); the partial-sum receive buffer and its staging copy are single-buffered (2 x 64 KB would not fit) behind a
+  // "receive buffer consumed" handshake (ps_free) and cp.async.bulk.wait_group.read
+  static constexpr bool BIG = H > 256;
+  static constexpr int TM_A = BIG ? 128 : 256, TM_COLS = 512;
+  static constexpr int MT_TM_LO = BIG ? 2 : MT;                   // M tiles whose lo plane is in tensor memory
+  __host__ __device__ static constexpr int tm_hi(int mt) { return BIG ? TM_A + mt * 64 : TM_A + (2 * mt) * 64; }
+  __host__ __device__ static constexpr int tm_lo(int mt) { return BIG ? TM_A + (MT + mt) * 64 : TM_A + (2 * mt + 1) * 64; }
+  static_assert(MT * NACC * NB <= TM_A, "accumulators overlap the weight tiles in tensor memory");
+  static constexpr int NBUF = BIG ? 1 : 2;
   static constexpr int OFF_PS = OFF_DG + 2 * DG_PLANE;            // [buf][src][n][32]
-  static constexpr int OFF_PSTAGE = OFF_PS + 2 * C * PS_SLOT;     // [dbuf][owner][n][32]
-  static constexpr int OFF_BAR = OFF_PSTAGE + 2 * C * PS_SLOT;
-  static constexpr int OFF_GSTAGE = OFF_BAR + 64;                 // [plane][k-chunk][n][8 bf16]: per-row dgin sums (repeat > 1)
-  static constexpr int BYTES = OFF_GSTAGE + 2 * DG_PLANE;
+  static constexpr int OFF_PSTAGE = OFF_PS + NBUF * C * PS_SLOT;  // [dbuf][owner][n][32]
+  static constexpr int OFF_BAR = OFF_PSTAGE + NBUF * C * PS_SLOT;
+  static constexpr int OFF_GSTAGE = OFF_BAR + 128;                // [plane][k-chunk][n][8 bf16]: per-row dgin sums (repeat > 1)
+  // lo planes of the W^T tiles that are not in tensor memory: per (tile, k-step) one 4 KB K-major block
+  // [2 k-chunks][16 row groups][8 rows][16 B] (descriptor LBO = 2048, SBO = 128)
+  static constexpr int OFF_WLO = OFF_GSTAGE + 2 * DG_PLANE;
+  static constexpr int BYTES = OFF_WLO + (MT - MT_TM_LO) * 8 * 4096;
   static_assert(BYTES <= 232448, "backward scan tile does not fit in 227 KB of shared memory");
+  static_assert(OFF_WLO % 128 == 0, "descriptor alignment");
 };
 
 template <int H, int NB>
@@ -609,7 +641,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   float* pstage = reinterpret_cast<float*>(smem + SM::OFF_PSTAGE);
   uint64_t* ps_full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);  // [2]
   uint64_t* mma_done = ps_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  uint64_t* ps_free = mma_done + 1;                                     // BIG only: C arrivals per step
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ps_free + 1);
   volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
   unsigned char* gst = smem + SM::OFF_GSTAGE;
   const int kt_k = 4 * H / 32;                                    // k tiles of the K-major image (gate columns / 32)
@@ -619,6 +652,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     tc::mbar_init(&ps_full[0], 1);
     tc::mbar_init(&ps_full[1], 1);
     tc::mbar_init(mma_done, 1);
+    tc::mbar_init(ps_free, C);
     tc::fence_mbar_init_cluster();
     *dead = 0;
   }
@@ -660,12 +694,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
           const float v1 = (j < H) ? __ldg(p.whh + (row0 + 1) * H + j) : 0.f;
           split_pack2(v0, v1, hi[i], lo[i]);
         }
-        tc::tmem_st_32x32b_x8(lane_base + SM::TM_A + (2 * mt + 0) * 64 + ks * 8, hi);
-        tc::tmem_st_32x32b_x8(lane_base + SM::TM_A + (2 * mt + 1) * 64 + ks * 8, lo);
+        tc::tmem_st_32x32b_x8(lane_base + SM::tm_hi(mt) + ks * 8, hi);
+        if (mt < SM::MT_TM_LO) {
+          tc::tmem_st_32x32b_x8(lane_base + SM::tm_lo(mt) + ks * 8, lo);
+        } else {   // lo plane of this tile -> shared memory, K-major core matrices: row = output unit within the tile
+          unsigned char* d = smem + SM::OFF_WLO + ((mt - SM::MT_TM_LO) * 8 + ks) * 4096 + (q * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
+          *reinterpret_cast<uint4*>(d) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(d + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
       }
     }
     tc::tmem_wait_st();
   }
+  tc::fence_proxy_async_smem();
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
@@ -673,6 +714,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
 
   const uint32_t idesc = tc::make_idesc_bf16_f32(128, NB);
   const uint64_t db_hi0 = tc::make_smem_desc(tc::smem_u32(dgs), NB * 16, 128);
+  const uint64_t wlo_desc0 = tc::make_smem_desc(tc::smem_u32(smem + SM::OFF_WLO), 2048, 128);
   const uint32_t slot_bytes = (uint32_t)n_valid * 128u;            // only rows that exist travel: [n][32 units] fp32
   const uint32_t step_tx = (uint32_t)C * slot_bytes;
 
@@ -751,7 +793,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
         float dh = phead[j];
         if (it > 0) {
 #pragma unroll
-          for (int src = 0; src < C; ++src) dh += ps[((buf * C + src) * NB + n) * 32 + lane];
+          for (int src = 0; src < C; ++src) dh += ps[(((SM::BIG ? 0 : buf) * C + src) * NB + n) * 32 + lane];
         }
         const float ig = pg[j][0], fg = pg[j][1], gg = pg[j][2], og = pg[j][3];
         const float tcn = fast_tanh(pc_new[j]);
@@ -846,6 +888,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     tc::fence_before_thread_sync();
     __syncthreads();
     if (s == 0) { store_dg(); break; }  // dh_{-1} is not needed: the initial state is data, not a parameter
+    if (SM::BIG && w_u == 1 && lane < C) {   // every thread of this CTA has consumed its receive buffer (phase `it`)
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc::mapa(tc::smem_u32(ps_free), (uint32_t)lane))
+                   : "memory");
+    }
 
     if (w_u == 0) {
       tc::fence_after_thread_sync();
@@ -855,12 +901,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t ta_hi = tmem_base + SM::TM_A + (2 * mt + 0) * 64 + ks * 8;
-          const uint32_t ta_lo = tmem_base + SM::TM_A + (2 * mt + 1) * 64 + ks * 8;
+          const uint32_t ta_hi = tmem_base + SM::tm_hi(mt) + ks * 8;
+          const uint32_t ta_lo = tmem_base + SM::tm_lo(mt) + ks * 8;
           const uint64_t db_hi = db_hi0 + (uint64_t)((ks * 2 * NB * 16) >> 4);
           const uint64_t db_lo = db_hi + (uint64_t)(SM::DG_PLANE >> 4);
           const uint32_t d = tmem_base + (mt * SM::NACC + (ks % SM::NACC)) * NB;
-          tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks >= SM::NACC);
+          if (mt < SM::MT_TM_LO) tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks >= SM::NACC);
+          else tc::mma_bf16_ss(d, wlo_desc0 + (uint64_t)((((mt - SM::MT_TM_LO) * 8 + ks) * 4096) >> 4), db_hi, idesc, ks >= SM::NACC);
           tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
           tc::mma_bf16_ts(d, ta_hi, db_hi, idesc, true);
         }
@@ -873,11 +920,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     if (!*dead) {
       if (!tc::mbar_wait(mma_done, it & 1)) { *dead = 1; atomicExch(err, 4); }
     }
+    if (SM::BIG && !*dead) {
+      // single receive / staging buffers: phase `it` of ps_free completes when every CTA of the cluster has consumed
+      // the sums of this step, i.e. (a) all my copies of the previous step have landed - the staging buffer may be
+      // overwritten - and (b) every receive buffer may be overwritten by the copies issued below
+      if (!tc::mbar_wait(ps_free, it & 1)) { *dead = 1; atomicExch(err, 7); }
+    }
     tc::fence_after_thread_sync();
     __syncwarp();
 
     // ---- partial sums -> staging [owner CTA][n][32 units]; lane = output unit j within the 128-row tile
-    float* pst = pstage + (size_t)(it & 1) * C * NB * 32;
+    float* pst = pstage + (size_t)(SM::BIG ? 0 : (it & 1)) * C * NB * 32;
     {
       const int q = w & 3;
       for (int idx = (w >> 2); idx < MT * RG; idx += TC_WARPS / 4) {
@@ -904,7 +957,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     if (w_u < C && tc::elect_one()) {  // reduce-scatter: my partials for owner w's units -> its slot [buf^1][my rank]
       const uint32_t d = w_u;
       const uint32_t src = tc::smem_u32(pst + (size_t)d * NB * 32);
-      const uint32_t dst_local = tc::smem_u32(ps + ((size_t)((buf ^ 1) * C + rank) * NB) * 32);
+      const uint32_t dst_local = tc::smem_u32(ps + ((size_t)((SM::BIG ? 0 : (buf ^ 1)) * C + rank) * NB) * 32);
       tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, slot_bytes, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
     }
 #pragma unroll
@@ -946,6 +999,7 @@ template <typename Kern, typename Params>
 int launch_cluster_tc(Kern kern, const Params& p, int cluster_size, int n_clusters, int smem_bytes, cudaStream_t stream,
                       int threads = TC_THREADS) {
   R2D2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (cluster_size > 8) R2D2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cluster_size * n_clusters);
   cfg.blockDim = dim3(threads);
@@ -969,6 +1023,7 @@ int launch_cluster_tc(Kern kern, const Params& p, int cluster_size, int n_cluste
 template <typename Kern>
 int max_active_clusters(Kern kern, int cluster_size, int smem_bytes) {
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (cluster_size > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cluster_size * 64);
   cfg.blockDim = dim3(TC_THREADS);
@@ -1012,9 +1067,11 @@ int fwd_tc(const ScanFwdParams& p_in, cudaStream_t stream) {
   p.rows_per_cluster = t.rows_per_cluster;
   if (t.nb == 16)
     return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 16>, p, H / 32, t.n_clusters, TcFwdSmem<H, 16>::BYTES, stream);
-  if (scan_pingpong_enabled())
-    return p.trace ? launch_cluster_tc(lstm_scan_fwd_pp_kernel<H, true>, p, H / 32, t.n_clusters, PpFwdSmem<H>::BYTES, stream, PP_THREADS)
-                   : launch_cluster_tc(lstm_scan_fwd_pp_kernel<H, false>, p, H / 32, t.n_clusters, PpFwdSmem<H>::BYTES, stream, PP_THREADS);
+  if constexpr (H <= 256) {
+    if (scan_pingpong_enabled())
+      return p.trace ? launch_cluster_tc(lstm_scan_fwd_pp_kernel<H, true>, p, H / 32, t.n_clusters, PpFwdSmem<H>::BYTES, stream, PP_THREADS)
+                     : launch_cluster_tc(lstm_scan_fwd_pp_kernel<H, false>, p, H / 32, t.n_clusters, PpFwdSmem<H>::BYTES, stream, PP_THREADS);
+  }
   return launch_cluster_tc(lstm_scan_fwd_tc_kernel<H, 32>, p, H / 32, t.n_clusters, TcFwdSmem<H, 32>::BYTES, stream);
 }
 template <int H>
@@ -1073,6 +1130,10 @@ int lstm_scan_max_active_clusters(int H, int nb, int backward) {
                                            : max_active_clusters(lstm_scan_fwd_tc_kernel<256, 16>, 8, TcFwdSmem<256, 16>::BYTES);
   if (H == 256 && nb == 32) return backward ? max_active_clusters(lstm_scan_bwd_tc_kernel<256, 32>, 8, TcBwdSmem<256, 32>::BYTES)
                                            : max_active_clusters(lstm_scan_fwd_tc_kernel<256, 32>, 8, TcFwdSmem<256, 32>::BYTES);
+  if (H == 512 && nb == 16) return backward ? max_active_clusters(lstm_scan_bwd_tc_kernel<512, 16>, 16, TcBwdSmem<512, 16>::BYTES)
+                                           : max_active_clusters(lstm_scan_fwd_tc_kernel<512, 16>, 16, TcFwdSmem<512, 16>::BYTES);
+  if (H == 512 && nb == 32) return backward ? max_active_clusters(lstm_scan_bwd_tc_kernel<512, 32>, 16, TcBwdSmem<512, 32>::BYTES)
+                                           : max_active_clusters(lstm_scan_fwd_tc_kernel<512, 32>, 16, TcFwdSmem<512, 32>::BYTES);
   if (H == 128 && nb == 16) return backward ? max_active_clusters(lstm_scan_bwd_tc_kernel<128, 16>, 4, TcBwdSmem<128, 16>::BYTES)
                                            : max_active_clusters(lstm_scan_fwd_tc_kernel<128, 16>, 4, TcFwdSmem<128, 16>::BYTES);
   return -1;
@@ -1084,6 +1145,7 @@ int lstm_scan_forward_tc(const ScanFwdParams& p, cudaStream_t stream) {
     case 64: return fwd_tc<64>(p, stream);
     case 128: return fwd_tc<128>(p, stream);
     case 256: return fwd_tc<256>(p, stream);
+    case 512: return fwd_tc<512>(p, stream);
     default: break;
   }
   set_last_error("tcgen05 scan: unsupported hidden size");
@@ -1096,6 +1158,7 @@ int lstm_scan_backward_tc(const ScanBwdParams& p, cudaStream_t stream) {
     case 64: return bwd_tc<64>(p, stream);
     case 128: return bwd_tc<128>(p, stream);
     case 256: return bwd_tc<256>(p, stream);
+    case 512: return bwd_tc<512>(p, stream);
     default: break;
   }
   set_last_error("tcgen05 scan: unsupported hidden size");

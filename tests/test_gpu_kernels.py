@@ -139,6 +139,10 @@ NET_CASES = [
     (3, 1, 128, 9, 6, 1, True, 0),          # Pendulum shape, A = 1
     (6, 2, 96, 5, 4, 1, True, 1),           # generic scan path (H not covered by the cluster kernels)
     (6, 2, 96, 5, 3, 2, False, 0),
+    (20, 4, 512, 12, 5, 1, True, 1),        # H = 512: cluster of 16 CTAs, one 16-row tile
+    (20, 4, 512, 40, 4, 2, False, 0),       # three clusters of 16 rows (ragged), double actor step
+    (376, 17, 512, 150, 3, 1, True, 1),     # cfg-3 widths, more rows than 8 resident clusters x 16 -> 32-row tiles
+    (33, 5, 512, 300, 3, 2, False, 0),      # 32-row tiles in two waves of clusters, repeat = 2
 ]
 
 

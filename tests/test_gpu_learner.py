@@ -101,30 +101,41 @@ def test_cfg2_full_size_against_port(eng_mod):
         print(f"cfg-2 iteration {it}: worst relative error {max(errs.values()):.3e}")
 
 
-def test_cfg3_shape_generic_hidden_512(eng_mod):
-    """BASELINE.json configs[2] shape (obs=376 act=17 hidden=512 seq_len=80 burn_in=40) at a reduced batch: hidden 512 is
-    outside the cluster kernels (4 MB of bf16x3 W_hh does not fit a cluster) and takes the generic per-step path."""
-    pc = ref_port.PathConfig(obs=376, act=17, hidden=512, batch=24, burn_in=40, learning=80, n_step=5)
+@pytest.mark.parametrize("batch", [24, 512])
+def test_cfg3_hidden_512_against_port(eng_mod, batch):
+    """BASELINE.json configs[2] (obs=376 act=17 hidden=512 seq_len=80 burn_in=40): the cluster-of-16 tcgen05 scan
+    (W_hh hi plane in tensor memory, lo plane split between tensor and shared memory) at the full batch of 512 and at a
+    batch that fills a single 16-row tile, against the CPU port of the reference on the same synthetic batch."""
+    import ctypes
+    from r2d2_b200 import native as nv
+    pc = ref_port.PathConfig(obs=376, act=17, hidden=512, batch=batch, burn_in=40, learning=80, n_step=5)
     torch.set_num_threads(max(1, min(32, torch.get_num_threads())))
     port = ref_port.PortLearner(pc, seed=2)
-    cfg = eng_mod.PathConfig(obs=376, act=17, hidden=512, batch=24, burn_in=40, learning=80, n_step=5)
+    cfg = eng_mod.PathConfig(obs=376, act=17, hidden=512, batch=batch, burn_in=40, learning=80, n_step=5)
     eng = eng_mod.LearnerEngine(cfg)
     sd = lambda m: {k: v.detach().numpy() for k, v in m.state_dict().items()}  # noqa: E731
     eng.load_state_dicts(sd(port.actor), sd(port.critic))
-    batch = ref_port.synthetic_batch(pc, seed=4)
-    ref = port.iteration(batch)
-    eng.set_batch(batch)
+    batch_np = ref_port.synthetic_batch(pc, seed=4)
+    ref = port.iteration(batch_np)
+    eng.set_batch(batch_np)
     eng.step()
     torch.cuda.synchronize()
+    status = ctypes.c_int(0)
+    nv.check(nv.lib().r2d2_scan_status(ctypes.byref(status), nv.current_stream()))
+    assert status.value == 0, f"a bounded mbarrier wait timed out inside a scan kernel (code {status.value})"
     errs = {"q": rel_l2(eng.q_value.cpu().numpy(), ref["q_value"]),
             "target": rel_l2(eng.target_q_value.cpu().numpy(), ref["target_q_value"]),
-            "prio": rel_l2(eng.priority.cpu().numpy(), ref["priority"])}
+            "prio": rel_l2(eng.priority.cpu().numpy(), ref["priority"]),
+            "critic_loss": abs(eng.losses[0].item() - ref["critic_loss"]) / abs(ref["critic_loss"]),
+            "actor_loss": abs(eng.losses[1].item() - ref["actor_loss"]) / abs(ref["actor_loss"])}
     for net in ("actor", "critic"):
-        gr = flat_sd(eng.views(net, "grads"))
+        gr, pa = flat_sd(eng.views(net, "grads")), flat_sd(eng.views(net))
         for k in eng_mod.PARAM_KEYS:
             errs[f"{net}_grad/{k}"] = rel_l2(gr[k], ref[f"{net}_grad"][k])
+            errs[f"{net}_after/{k}"] = rel_l2(pa[k], ref[f"{net}_after"][k])
     bad = {k: v for k, v in errs.items() if not v < TOL}
     assert not bad, bad
+    print(f"cfg-3 batch {batch}: worst relative error {max(errs.values()):.3e}")
 
 
 def test_hard_target_update(eng_mod):

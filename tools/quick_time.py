@@ -27,7 +27,11 @@ def run(obs, act, hidden, batch, burn_in, learning, iters=10):
            "seq_steps_per_s": batch * learning / (tot.sum() * 1e-3), "launches": eng.launches_per_iteration}
     print(json.dumps(out)); return out
 
+CFGS = {"cfg1": (24, 6, 128, 32, 20, 40), "cfg2": (17, 6, 256, 256, 40, 80), "cfg3": (376, 17, 512, 512, 40, 80),
+        "cfg3s": (376, 17, 512, 64, 40, 80)}
+
 if __name__ == "__main__":
-    res = [run(24, 6, 128, 32, 20, 40), run(17, 6, 256, 256, 40, 80)]
+    names = sys.argv[1:] or ["cfg1", "cfg2"]
+    res = [run(*CFGS[n], iters=5 if n.startswith("cfg3") else 10) for n in names]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "quick_time.json"), "w"))
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "quick_time_" + "_".join(names) + ".json"), "w"))
