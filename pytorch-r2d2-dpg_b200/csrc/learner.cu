@@ -65,6 +65,8 @@ int learner_create(Learner** out, const r2d2_learner_config* cfg) {
   l->ws_c1 = ChainWs::carve(take(ws_c1), l->critic_sh, Tc, B, 1);
   l->ws_a1 = ChainWs::carve(take(ws_a1), l->actor_sh, L, B, 2);
   l->ws_c2 = ChainWs::carve(take(ws_c2), l->critic_sh, L, B, 1);
+  l->ws_ta.inference_only = true;  // target nets: no BPTT, the scan keeps only what the heads read (learner.py:94-95,106)
+  l->ws_tc.inference_only = true;
   l->ws_c1.keep_z1_image = true;   // chains whose weights get gradients: the l1 kernel also leaves z1 as the B operand of dW_ih
   l->ws_a1.keep_z1_image = true;
   *out = l;

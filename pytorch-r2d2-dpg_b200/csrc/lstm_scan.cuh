@@ -20,6 +20,10 @@ struct ScanFwdParams {
   float* scratch = nullptr;     // generic path only: [B,4H]
   int rows_per_cluster = 0;     // set by the tcgen05 dispatcher: batch rows owned by one cluster (<= its N tile)
   long long* trace = nullptr;   // debug: [grid][S][8] globaltimer stamps written by thread 0 of every CTA (tcgen05 kernel)
+  unsigned char* xchg = nullptr;   // set by the tcgen05 dispatcher (H = 512): global scratch of the h_t exchange through L2
+  int no_save = 0;                 // 1: chain is never back-propagated (target nets): gates / cs need not be stored (hs, head_in
+                                   // still are); honoured by the H = 512 kernel, ignored elsewhere
+  int dbg = 0;                     // dev only (env R2D2_SCAN_DBG, honoured by the trace build of the H = 512 kernel)
 };
 
 struct ScanBwdParams {
@@ -44,6 +48,7 @@ struct ScanBwdParams {
                                         // (pass img_mn_dg again when repeat == 1: the two tensors coincide)
   int skip_fp32 = 0;                    // 1: do not store fp32 dgates / dgin (every consumer reads the images)
   int rows_per_cluster = 0;        // set by the tcgen05 dispatcher
+  unsigned char* xchg = nullptr;   // set by the tcgen05 dispatcher (H = 512): global scratch of the partial-sum exchange through L2
 };
 
 // true when lstm_scan_backward will honour img_* (persistent tcgen05 kernels selected for this hidden size)

@@ -30,6 +30,7 @@ namespace cg = cooperative_groups;
 namespace r2d2 {
 
 int* scan_error_flag();  // device int, 0 = ok (defined below)
+unsigned char* scan_xchg_scratch(size_t* bytes);   // per-device global scratch of the H = 512 exchanges through L2
 
 namespace {
 
@@ -889,8 +890,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     __syncthreads();
     if (s == 0) { store_dg(); break; }  // dh_{-1} is not needed: the initial state is data, not a parameter
     if (SM::BIG && w_u == 1 && lane < C) {   // every thread of this CTA has consumed its receive buffer (phase `it`)
-      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc::mapa(tc::smem_u32(ps_free), (uint32_t)lane))
-                   : "memory");
+      tc::mbar_arrive_remote_relaxed(ps_free, (uint32_t)lane);   // relaxed: the release form is a MEMBAR.GPU behind this thread's dG stores
     }
 
     if (w_u == 0) {
@@ -958,7 +958,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       const uint32_t d = w_u;
       const uint32_t src = tc::smem_u32(pst + (size_t)d * NB * 32);
       const uint32_t dst_local = tc::smem_u32(ps + ((size_t)((SM::BIG ? 0 : (buf ^ 1)) * C + rank) * NB) * 32);
-      tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, slot_bytes, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
+      if (SM::BIG && p.xchg) {
+        // through L2 (profiles/r02_xchg_bench.txt): store my partials for owner d, wait for the writes, then a bulk load
+        // "multicast" to that single CTA: it lands at the same CTA-relative offset in d and completes d's mbarrier
+        unsigned char* g = p.xchg + ((((size_t)(blockIdx.x / C) * 2 + (it & 1)) * C + rank) * C + d) * (size_t)(NB * 128);
+        tc::bulk_store_s2g(g, src, slot_bytes);
+        tc::bulk_commit_wait_all();
+        tc::bulk_copy_g2s_multicast(dst_local, g, slot_bytes, tc::smem_u32(&ps_full[buf ^ 1]), (uint16_t)(1u << d));
+      } else {
+        tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, slot_bytes, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
+      }
     }
 #pragma unroll
     for (int j = 0; j < NT; ++j) {   // rotate the pipeline registers
@@ -986,6 +995,350 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       if (p.dbias2) atomicAdd(p.dbias2 + q * H + ug, t);
     }
   }
+  if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, SM::TM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, H = 512: cluster of 16 CTAs, up to 80 batch rows per cluster as two ping-pong sub-tiles of <= 40 rows.
+//
+// What differs from the kernels above (measured reasons in profiles/r02_*):
+//  * only 7 clusters of 16 are resident on a B200 (GPC geometry), so 512 rows are spread as 7 x 74 in ONE wave;
+//  * the h_t all-gather goes THROUGH L2: the CTA's slice of a row group (1 KB: 32 units x 8 rows x hi/lo) is bulk-stored
+//    to a global scratch line and re-loaded by one MULTICAST bulk copy that lands in all 16 CTAs and completes
+//    transaction bytes on each CTA's mbarrier (12 -> ~95 B/clk/SM against shared->remote-shared copies);
+//  * the h operand of a sub-tile (40 rows x 512 x hi/lo = 80 KB) is single-buffered: a source may overwrite it only
+//    after every CTA of the cluster has retired the MMAs that read it (buf_free: 16 remote arrivals per step);
+//  * gate rows are PERMUTED in tensor memory (lane = 4 * unit + gate inside a lane quarter), so the four gates of a
+//    cell sit in four adjacent lanes of one warp: the accumulator readback is transposed with eight warp shuffles -
+//    no shared-memory tile, no block barrier between readback and cell math;
+//  * dedicated exchange warps (one per row group) own the store -> wait -> multicast-load chain; cell warps only
+//    arrive on a named barrier; a dedicated warp issues the MMAs (96 per sub-tile step: K = 512, three passes, the
+//    last 12 k-steps of the W_hh lo plane come from shared memory).
+// ------------------------------------------------------------------------------------------------
+constexpr int BIG_CELL_WARPS = 20, BIG_THREADS = (BIG_CELL_WARPS + 1) * 32;   // 672: 5 row groups x 4 lane quarters + MMA warp
+
+struct BigFwdSmem {
+  static constexpr int H = 512, C = 16, KC = H / 8, KS = H / 16;
+  static constexpr int SLICE = 1024, RG_BYTES = C * SLICE;
+  static constexpr int MAX_RG = 5, MAX_ROWS = 8 * MAX_RG;          // per sub-tile
+  static constexpr int SUB_BYTES = MAX_RG * RG_BYTES;              // 80 KB
+  static constexpr int NCOL = 48;                                  // accumulator columns per sub-tile (N <= 48)
+  static constexpr int TM_A_HI = 2 * NCOL, TM_A_LO = TM_A_HI + H / 2, TM_COLS = 512;
+  static constexpr int KS_TM_LO = (TM_COLS - TM_A_LO) / 8, KS_TAIL = KS - KS_TM_LO;   // 20 / 12
+  static constexpr int OFF_HB = 0;                                 // [sub][row group][slice][plane][4 chunks][8][16 B]
+  static constexpr int OFF_WTAIL = OFF_HB + 2 * SUB_BYTES;         // [k-step][2 k-chunks][16 row groups][8][16 B]
+  static constexpr int OFF_HSTAGE = OFF_WTAIL + KS_TAIL * 4096;    // [sub][row group][SLICE]
+  static constexpr int OFF_BAR = OFF_HSTAGE + 2 * MAX_RG * SLICE;  // h_full[2], mma_done[2], buf_free[2], tmem slot, dead
+  static constexpr int BYTES = OFF_BAR + 128;
+  static constexpr int XCHG_PER_CLUSTER = 2 * 2 * C * MAX_RG * SLICE;   // [step parity][sub][rank][row group][1 KB]
+  static_assert(BYTES <= 232448, "H = 512 forward scan does not fit in shared memory");
+};
+
+#define BIG_STAMP(cond, slot) do { if (TRACE && (cond)) p.trace[(((size_t)blockIdx.x * S + s) * 2 + sub) * 8 + (slot)] = gtime(); } while (0)
+
+// two activations with ONE reciprocal: 1/(1+ea) and 1/(1+eb) from rcp((1+ea)(1+eb)); the MUFU pipe (one warp
+// instruction per 8 clocks and scheduler) and the issue slots bound the cell phase of this kernel, not the FP32 math.
+// x <= 0 arguments are clamped at -30 / scale so that the product of two denominators stays finite.
+__device__ __forceinline__ void sigmoid_pair(float xa, float xb, float neg_scale_log2e, float& sa, float& sb) {
+  const float ea = tc::ex2_approx(fminf(xa * neg_scale_log2e, 43.f)), eb = tc::ex2_approx(fminf(xb * neg_scale_log2e, 43.f));
+  const float da = 1.f + ea, db = 1.f + eb;
+  const float r = tc::rcp_approx(da * db);
+  sa = r * db;
+  sb = r * da;
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(BIG_THREADS, 1) lstm_scan_fwd_big_kernel(ScanFwdParams p, int* err) {
+  using SM = BigFwdSmem;
+  constexpr int H = SM::H, C = SM::C, KC = SM::KC, KS = SM::KS;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cl = blockIdx.x / C;
+  const int b0 = cl * p.rows_per_cluster;
+  const int b_end = min(p.B, b0 + p.rows_per_cluster);
+  const int n_rows = b_end - b0;                                   // 1..80
+  const int n_sub = n_rows > 8 ? 2 : 1;
+  const int rows0 = n_sub == 2 ? (n_rows + 1) / 2 : n_rows;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int B = p.B, S = p.T * p.repeat;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* hb = smem + SM::OFF_HB;
+  unsigned char* hstage = smem + SM::OFF_HSTAGE;
+  uint64_t* h_full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);   // [sub]
+  uint64_t* mma_done = h_full + 2;                                      // [sub]
+  uint64_t* buf_free = mma_done + 2;                                    // [sub]: C arrivals per step
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_free + 2);
+  volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int rows_of[2] = {rows0, n_rows - rows0};
+  const int row0_of[2] = {0, rows0};
+  const int rgv_of[2] = {(rows0 + 7) >> 3, (n_rows - rows0 + 7) >> 3};
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&h_full[i], 1); tc::mbar_init(&mma_done[i], 1); tc::mbar_init(&buf_free[i], C); }
+    tc::fence_mbar_init_cluster();
+    *dead = 0;
+  }
+  if (w == 1) { __syncwarp(); tc::tmem_alloc(tmem_slot, SM::TM_COLS); }
+  // ---- initial h tiles (all 512 units of my cluster's rows; zeros where no row exists) -> operand buffers
+  for (int idx = tid; idx < 2 * SM::MAX_ROWS * KC; idx += BIG_THREADS) {
+    const int sub = idx / (SM::MAX_ROWS * KC), rem = idx % (SM::MAX_ROWS * KC);
+    const int n = rem % SM::MAX_ROWS, kc = rem / SM::MAX_ROWS;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (sub < n_sub && n < rows_of[sub] && p.h0) {
+      const float* src = p.h0 + (size_t)(b0 + row0_of[sub] + n) * H + kc * 8;
+      v0 = __ldg(reinterpret_cast<const float4*>(src));
+      v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+    }
+    unsigned char* dst = hb + sub * SM::SUB_BYTES + (n >> 3) * SM::RG_BYTES + (kc >> 2) * SM::SLICE + (kc & 3) * 128 + (n & 7) * 16;
+    split8_store(v0, v1, dst, dst + 512);
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // ---- W_hh slice -> tensor memory.  Lane L of quarter k = L / 32: unit = 8 k + (L % 32) / 4, gate = L % 4.
+  if (w < BIG_CELL_WARPS) {
+    const int k = w & 3;
+    const int unit = k * 8 + (lane >> 2), gate = lane & 3;
+    const float* wrow = p.whh + (size_t)(gate * H + rank * 32 + unit) * H;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(k * 32) << 16);
+    __syncwarp();
+#pragma unroll 1
+    for (int ks = (w >> 2); ks < KS; ks += BIG_CELL_WARPS / 4) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wrow + ks * 16 + i * 4));
+        split_pack2(v.x, v.y, hi[2 * i], lo[2 * i]);
+        split_pack2(v.z, v.w, hi[2 * i + 1], lo[2 * i + 1]);
+      }
+      tc::tmem_st_32x32b_x8(lane_base + SM::TM_A_HI + ks * 8, hi);
+      if (ks < SM::KS_TM_LO) {
+        tc::tmem_st_32x32b_x8(lane_base + SM::TM_A_LO + ks * 8, lo);
+      } else {
+        unsigned char* d = smem + SM::OFF_WTAIL + (ks - SM::KS_TM_LO) * 4096 + (k * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(d + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+    }
+    tc::tmem_wait_st();
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  cluster.sync();
+
+  const uint32_t hb_addr = tc::smem_u32(hb);
+  const size_t gstride = (size_t)4 * H;
+
+  if (w_u == BIG_CELL_WARPS) {
+    // ================= MMA warp =================
+    const uint64_t db0 = tc::make_smem_desc(hb_addr, 128, SM::RG_BYTES);
+    const uint64_t wtail_desc0 = tc::make_smem_desc(tc::smem_u32(smem + SM::OFF_WTAIL), 2048, 128);
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        if (sub >= n_sub) break;
+        BIG_STAMP(lane == 0, 0);
+        if (s > 0 && !*dead) {
+          if (!tc::mbar_wait(&h_full[sub], (s - 1) & 1)) { *dead = 1; atomicExch(err, 8); }
+        }
+        __syncwarp();
+        BIG_STAMP(lane == 0, 1);
+        tc::fence_after_thread_sync();
+        if (tc::elect_one()) {
+          if (s + 1 < S) tc::mbar_arrive_expect_tx(&h_full[sub], (uint32_t)(C * rgv_of[sub] * SM::SLICE));   // h_s of all 16 CTAs
+          const uint32_t idesc = tc::make_idesc_bf16_f32(128, 16 * ((rows_of[sub] + 15) >> 4));
+          const uint64_t db_sub = db0 + (uint64_t)((sub * SM::SUB_BYTES) >> 4);
+          const uint32_t d = tmem_base + sub * SM::NCOL;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t ta_hi = tmem_base + SM::TM_A_HI + ks * 8, ta_lo = tmem_base + SM::TM_A_LO + ks * 8;
+            const uint64_t db_hi = db_sub + (uint64_t)(((ks >> 1) * SM::SLICE + (ks & 1) * 256) >> 4);
+            const uint64_t db_lo = db_hi + (uint64_t)(512 >> 4);
+            if (ks < SM::KS_TM_LO) tc::mma_bf16_ts(d, ta_lo, db_hi, idesc, ks != 0);
+            else tc::mma_bf16_ss(d, wtail_desc0 + (uint64_t)(((ks - SM::KS_TM_LO) * 4096) >> 4), db_hi, idesc, true);
+            tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
+            tc::mma_bf16_ts(d, ta_hi, db_hi, idesc, true);
+          }
+          tc::mma_commit(&mma_done[sub]);
+        }
+        __syncwarp();
+        BIG_STAMP(lane == 0, 2);
+      }
+    }
+  } else {
+    // ================= cell warps: row group j = w / 4, lane quarter k = w % 4 (units 8k..8k+7 of this CTA) ============
+    // lane = 4 * unit + gate: the thread activates ITS gate for the 8 rows of the group, then the four lanes of a unit
+    // swap 2-row blocks (8 shuffles) and each finishes the cells of rows 2 pq, 2 pq + 1
+    const int k = w & 3, j = w >> 2;
+    const int u8 = lane >> 2, pq = lane & 3;
+    const int ug = rank * 32 + k * 8 + u8;          // global hidden unit
+    const bool hiq = (pq & 2) != 0, odd = (pq & 1) != 0;
+    const float sc = pq == 2 ? 2.f : 1.f;           // gate 2 is tanh(x) = 2 sigmoid(2x) - 1
+    const float nsl = -1.4426950408889634f * sc, off = 1.f - sc;
+    unsigned char* xbase = p.xchg + (size_t)cl * SM::XCHG_PER_CLUSTER;
+    float cst[2][2];
+    bool act_of[2];
+    const float* gin_ptr[2];      // gin of (row j*8 + 0, gate pq, unit) at input row t
+    float* gate_ptr[2];           // gates of the same element at step s
+    float* hs_ptr[2];             // hs of (row j*8 + 2 pq, unit) at slot s + 1
+    float* head_ptr[2];
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      act_of[sub] = sub < n_sub && j < rgv_of[sub];
+      const size_t brow = (size_t)(b0 + row0_of[sub] + j * 8);
+      gin_ptr[sub] = p.gin + brow * gstride + pq * H + ug;
+      gate_ptr[sub] = p.gates + brow * gstride + pq * H + ug;
+      hs_ptr[sub] = p.hs + ((size_t)B + brow + 2 * pq) * H + ug;
+      head_ptr[sub] = p.head_in ? p.head_in + (brow + 2 * pq) * H + ug : nullptr;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n = j * 8 + 2 * pq + i;
+        cst[sub][i] = 0.f;
+        if (act_of[sub] && n < rows_of[sub]) {
+          const size_t b = (size_t)(b0 + row0_of[sub] + n);
+          const float hv = p.h0 ? __ldg(p.h0 + b * H + ug) : 0.f;
+          const float cv = p.c0 ? __ldg(p.c0 + b * H + ug) : 0.f;
+          p.hs[b * H + ug] = hv;
+          p.cs[b * H + ug] = cv;
+          cst[sub][i] = cv;
+        }
+      }
+    }
+    const ptrdiff_t cs_off = p.cs - p.hs;
+    const size_t gate_step = (size_t)B * gstride, h_step = (size_t)B * H;
+    int rep = 0;
+    for (int s = 0; s < S; ++s) {
+      const bool last_rep = rep == p.repeat - 1;
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        if (!act_of[sub]) continue;
+        const int nrow = rows_of[sub] - j * 8;      // rows of this group that exist (>= 1)
+        // input projection of this gate for the 8 rows: issued before the wait, the MMAs take longer than the loads
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (i < nrow && !(TRACE && (p.dbg & 2))) ? gin_ptr[sub][(size_t)i * gstride] : 0.f;   // plain loads: gates may alias gin
+        if (!*dead) {
+          if (!tc::mbar_wait(&mma_done[sub], s & 1)) { *dead = 1; atomicExch(err, 10); }
+        }
+        BIG_STAMP(tid == 0, 3);
+        if (w_u == 0 && lane < C) tc::mbar_arrive_remote_relaxed(&buf_free[sub], (uint32_t)lane);   // this CTA's MMAs of (s, sub) have retired
+        tc::fence_after_thread_sync();
+        __syncwarp();
+        {
+          float v[8];
+          tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(k * 32) << 16) + (uint32_t)(sub * SM::NCOL + j * 8), v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] += v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          float sa, sb;
+          sigmoid_pair(x[i], x[i + 1], nsl, sa, sb);
+          x[i] = fmaf(sc, sa, off);
+          x[i + 1] = fmaf(sc, sb, off);
+        }
+        // 4 x 4 transpose of 2-row blocks among the four lanes of a unit: lane pq ends up with all gates of rows 2pq, 2pq+1
+        float kk[4], rc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float snd = hiq ? x[i] : x[4 + i];
+          kk[i] = hiq ? x[4 + i] : x[i];
+          rc[i] = __shfl_xor_sync(0xffffffffu, snd, 2);            // gate pq^2, rows 4*(pq>>1) + i
+        }
+        float cn[2], hn[2];
+        unsigned char* hs_buf = hstage + (sub * SM::MAX_RG + j) * SM::SLICE;
+        float a0[2], a1[2], a2[2], a3[2];                          // gates pq, pq^2, pq^1, pq^3 of rows 2pq + i
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float s1 = odd ? kk[i] : kk[2 + i];
+          const float s2 = odd ? rc[i] : rc[2 + i];
+          a0[i] = odd ? kk[2 + i] : kk[i];
+          a1[i] = odd ? rc[2 + i] : rc[i];
+          a2[i] = __shfl_xor_sync(0xffffffffu, s1, 1);
+          a3[i] = __shfl_xor_sync(0xffffffffu, s2, 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          // lane 0: [i g f o], 1: [f o i g], 2: [g i o f], 3: [o f g i]  ->  i*g = u*v, (f, o) = (xx, yy) swapped on lanes 2, 3
+          const float u = odd ? a2[i] : a0[i], vv = odd ? a3[i] : a1[i];
+          const float xx = odd ? a0[i] : a2[i], yy = odd ? a1[i] : a3[i];
+          const float fg = hiq ? yy : xx, og = hiq ? xx : yy;
+          cn[i] = fmaf(fg, cst[sub][i], u * vv);
+          cst[sub][i] = cn[i];
+          hn[i] = og;
+        }
+        {
+          float ta, tb;                                            // tanh(c) = 2 sigmoid(2c) - 1
+          sigmoid_pair(cn[0], cn[1], -2.8853900817779268f, ta, tb);
+          hn[0] *= fmaf(2.f, ta, -1.f);
+          hn[1] *= fmaf(2.f, tb, -1.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+          if (2 * pq + i < nrow) split_bf16(hn[i], hi, lo);
+          unsigned char* dst = hs_buf + k * 128 + (2 * pq + i) * 16 + u8 * 2;   // [plane][chunk = k][row][unit % 8]
+          *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(dst + 512) = lo;
+        }
+        BIG_STAMP(tid == 0, 4);
+        if (s + 1 < S) {
+          tc::fence_proxy_async_smem();
+          const int bar_id = 1 + sub * SM::MAX_RG + j;
+          if (k == 0) {   // this warp hands the row group's slice to the cluster: store -> L2 -> multicast load into all 16 CTAs
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (tc::elect_one()) {
+              unsigned char* g = xbase + ((size_t)(((s & 1) * 2 + sub) * C + rank) * SM::MAX_RG + j) * SM::SLICE;
+              tc::bulk_store_s2g(g, tc::smem_u32(hs_buf), SM::SLICE);
+              tc::bulk_commit_wait_all();
+              BIG_STAMP(j == 0, 6);
+              if (!*dead) {   // every CTA of the cluster has retired the MMAs of step s that read this sub-tile's operand buffer
+                if (!tc::mbar_wait(&buf_free[sub], s & 1)) { *dead = 1; atomicExch(err, 9); }
+              }
+              tc::bulk_copy_g2s_multicast(hb_addr + sub * SM::SUB_BYTES + j * SM::RG_BYTES + rank * SM::SLICE, g, SM::SLICE,
+                                          tc::smem_u32(&h_full[sub]), (uint16_t)0xFFFF);
+              BIG_STAMP(j == 0, 7);
+            }
+            __syncwarp();
+          } else {
+            asm volatile("bar.arrive %0, 128;" ::"r"(bar_id) : "memory");
+          }
+        }
+        // ---- saved activations: off the serial chain
+        if (!(TRACE && (p.dbg & 1))) {
+          if (!p.no_save) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i < nrow) gate_ptr[sub][(size_t)i * gstride] = x[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (2 * pq + i < nrow) {
+              float* ho = hs_ptr[sub] + (size_t)i * H;
+              ho[0] = hn[i];
+              if (!p.no_save) ho[cs_off] = cn[i];
+              if (head_ptr[sub] && last_rep) head_ptr[sub][(size_t)i * H] = fast_tanh(hn[i]);
+            }
+        }
+        gate_ptr[sub] += gate_step;
+        hs_ptr[sub] += h_step;
+        if (last_rep) {
+          gin_ptr[sub] += gate_step;
+          if (head_ptr[sub]) head_ptr[sub] += h_step;
+        }
+      }
+      rep = last_rep ? 0 : rep + 1;
+    }
+  }
+  tc::fence_before_thread_sync();
+  cluster.sync();
   if (w == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, SM::TM_COLS); }
 }
 
@@ -1021,12 +1374,12 @@ int launch_cluster_tc(Kern kern, const Params& p, int cluster_size, int n_cluste
 
 // how many clusters of this kernel the device can keep resident at once (GPC geometry decides, not just SM count)
 template <typename Kern>
-int max_active_clusters(Kern kern, int cluster_size, int smem_bytes) {
+int max_active_clusters(Kern kern, int cluster_size, int smem_bytes, int threads = TC_THREADS) {
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (cluster_size > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cluster_size * 64);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1059,8 +1412,42 @@ Tiling pick_tiling(int B, K16 k16, int smem16, K32 k32, int smem32) {
   return {32, rows, ceil_div(B, rows)};
 }
 
+// the H = 512 kernels exchange through L2 (env R2D2_SCAN_L2XCHG=0: shared->remote-shared copies, the A/B fallback)
+bool scan_l2_exchange_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("R2D2_SCAN_L2XCHG"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+int fwd_big(const ScanFwdParams& p_in, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if (!scan_l2_exchange_enabled()) return R2D2_OK;
+  static int fit = -2;
+  if (fit == -2) fit = max_active_clusters(lstm_scan_fwd_big_kernel<false>, 16, BigFwdSmem::BYTES, BIG_THREADS);
+  const int resident = fit > 0 ? fit : 7;
+  const int max_rows = 2 * BigFwdSmem::MAX_ROWS;
+  int rows = ceil_div(p_in.B, resident);
+  if (rows > max_rows) rows = ceil_div(p_in.B, ceil_div(p_in.B, max_rows));   // several waves of full clusters
+  const int n_clusters = ceil_div(p_in.B, rows);
+  size_t cap = 0;
+  unsigned char* scratch = scan_xchg_scratch(&cap);
+  if (!scratch || (size_t)n_clusters * BigFwdSmem::XCHG_PER_CLUSTER > cap) return R2D2_OK;
+  ScanFwdParams p = p_in;
+  p.rows_per_cluster = rows;
+  p.xchg = scratch;
+  if (const char* e = getenv("R2D2_SCAN_DBG")) p.dbg = atoi(e);
+  *handled = true;
+  return p.trace ? launch_cluster_tc(lstm_scan_fwd_big_kernel<true>, p, 16, n_clusters, BigFwdSmem::BYTES, stream, BIG_THREADS)
+                 : launch_cluster_tc(lstm_scan_fwd_big_kernel<false>, p, 16, n_clusters, BigFwdSmem::BYTES, stream, BIG_THREADS);
+}
+
 template <int H>
 int fwd_tc(const ScanFwdParams& p_in, cudaStream_t stream) {
+  if constexpr (H == 512) {
+    bool handled = false;
+    R2D2_TRY(fwd_big(p_in, stream, &handled));
+    if (handled) return R2D2_OK;
+  }
   ScanFwdParams p = p_in;
   const Tiling t = pick_tiling<H>(p.B, lstm_scan_fwd_tc_kernel<H, 16>, TcFwdSmem<H, 16>::BYTES,
                                   lstm_scan_fwd_tc_kernel<H, 32>, TcFwdSmem<H, 32>::BYTES);
@@ -1095,6 +1482,11 @@ int bwd_tc(const ScanBwdParams& p_in, cudaStream_t stream) {
   const Tiling t = pick_tiling<H>(p.B, lstm_scan_bwd_tc_kernel<H, 16>, TcBwdSmem<H, 16>::BYTES,
                                   lstm_scan_bwd_tc_kernel<H, 32>, TcBwdSmem<H, 32>::BYTES);
   p.rows_per_cluster = t.rows_per_cluster;
+  if constexpr (H == 512) {
+    size_t cap = 0;
+    unsigned char* scratch = scan_l2_exchange_enabled() ? scan_xchg_scratch(&cap) : nullptr;
+    if (scratch && (size_t)t.n_clusters * 2 * 16 * 16 * (size_t)(t.nb * 128) <= cap) p.xchg = scratch;
+  }
   if (t.nb == 16)
     return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 16>, p, H / 32, t.n_clusters, TcBwdSmem<H, 16>::BYTES, stream);
   return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 32>, p, H / 32, t.n_clusters, TcBwdSmem<H, 32>::BYTES, stream);
@@ -1115,6 +1507,25 @@ int* scan_error_flag() {   // one flag per device (a process may drive several G
   cudaMemset(flag, 0, sizeof(int));
   flags[dev] = flag;
   return flag;
+}
+
+// One scratch block per device: the scans of a device are stream-ordered behind each other (one learner stream); the
+// exchange lines are double-buffered by step parity inside a launch and every launch rewrites what it reads.
+unsigned char* scan_xchg_scratch(size_t* bytes) {
+  static std::mutex mu;
+  static std::map<int, unsigned char*> bufs;
+  constexpr size_t BYTES = (size_t)80 << 20;
+  if (bytes) *bytes = BYTES;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = bufs.find(dev);
+  if (it != bufs.end()) return it->second;
+  unsigned char* b = nullptr;
+  if (cudaMalloc(&b, BYTES) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  cudaMemset(b, 0, BYTES);
+  bufs[dev] = b;
+  return b;
 }
 
 int lstm_scan_error_status(int* out, cudaStream_t stream) {

@@ -100,6 +100,7 @@ int net_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, const 
   sp.gates = ws.gates; sp.hs = ws.hs; sp.cs = ws.cs;
   sp.head_in = s.critic ? nullptr : ws.head_in;
   sp.T = T; sp.B = B; sp.H = H; sp.repeat = repeat; sp.scratch = ws.scratch;
+  sp.no_save = ws.inference_only ? 1 : 0;
   return lstm_scan_forward(sp, stream);
 }
 

@@ -47,6 +47,7 @@ struct ChainWs {
   unsigned char* img_mn_dg = nullptr;   // dgates, MN-major tiles (A of dW_hh)
   unsigned char* img_mn_gin = nullptr;  // dgin, MN-major tiles (A of dW_ih); == img_mn_dg when repeat == 1
   unsigned char* img_z_mn = nullptr;    // z1, MN-major tiles (B of dW_ih), written by the l1 kernel when `keep_z1_image`
+  bool inference_only = false;          // set by the owner of a chain that is never back-propagated (target nets)
   bool keep_z1_image = false;           // set by the owner of a chain whose weights get gradients (learner: critic, actor)
   static size_t floats(const NetShape& s, int T, int B, int repeat);
   static ChainWs carve(float* base, const NetShape& s, int T, int B, int repeat);

@@ -173,5 +173,35 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem_addr, const void
                : "memory");
 }
 
+// ---- exchange through L2 (measured, profiles/r02_xchg_bench.txt: shared->remote-shared bulk copies move ~12 B/clk/SM
+// inside a cluster of 16; a bulk store to global followed by a MULTICAST bulk load moves ~95 B/clk/SM with ~900
+// cycles of latency).  The store and the load are issued by the same thread; wait_group 0 (not .read) waits until the
+// writes are performed, so the load that follows reads them from L2.
+__device__ __forceinline__ void bulk_store_s2g(void* dst_global, uint32_t src_smem_addr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// global -> the SAME CTA-relative shared offset (data and mbarrier) in every CTA of the cluster selected by `cta_mask`
+__device__ __forceinline__ void bulk_copy_g2s_multicast(uint32_t dst_smem_addr, const void* src_global, uint32_t bytes,
+                                                        uint32_t mbar_smem_addr, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   dst_smem_addr),
+               "l"(src_global), "r"(bytes), "r"(mbar_smem_addr), "h"(cta_mask)
+               : "memory");
+}
+// arrive (count 1) on an mbarrier of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa(smem_u32(local_bar), rank)) : "memory");
+}
+// same without release semantics: a pure "event happened" signal (the release form waits for every earlier memory
+// operation of the thread - e.g. global stores in flight - to be performed at cluster scope: ~1 us on the serial chain)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* local_bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa(smem_u32(local_bar), rank)) : "memory");
+}
+
 }  // namespace tc
 }  // namespace r2d2
