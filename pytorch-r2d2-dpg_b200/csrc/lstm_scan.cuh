@@ -49,6 +49,7 @@ struct ScanBwdParams {
   int skip_fp32 = 0;                    // 1: do not store fp32 dgates / dgin (every consumer reads the images)
   int rows_per_cluster = 0;        // set by the tcgen05 dispatcher
   unsigned char* xchg = nullptr;   // set by the tcgen05 dispatcher (H = 512): global scratch of the partial-sum exchange through L2
+  int dbg = 0;                     // dev only (env R2D2_SCAN_DBG): 1 = skip the dG stores, 2 = skip the saved-activation loads
 };
 
 // true when lstm_scan_backward will honour img_* (persistent tcgen05 kernels selected for this hidden size)

@@ -645,6 +645,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   uint64_t* ps_free = mma_done + 1;                                     // BIG only: C arrivals per step
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ps_free + 1);
   volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  uint64_t* mma_tile = ps_free + 2;                                     // BIG only: [MT] one completion barrier per M tile
   unsigned char* gst = smem + SM::OFF_GSTAGE;
   const int kt_k = 4 * H / 32;                                    // k tiles of the K-major image (gate columns / 32)
   const int kt_mn_dg = (S * B + 31) / 32, kt_mn_gin = (p.T * B + 31) / 32;
@@ -654,6 +655,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     tc::mbar_init(&ps_full[1], 1);
     tc::mbar_init(mma_done, 1);
     tc::mbar_init(ps_free, C);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&mma_tile[i], 1);
     tc::fence_mbar_init_cluster();
     *dead = 0;
   }
@@ -749,7 +751,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       c[j] = hd[j] = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) g[j][q] = 0.f;
-      if (any && rowon[j]) {
+      if (any && rowon[j] && !(p.dbg & 2)) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) g[j][q] = gates_nx[j][q * H];
         c[j] = __ldg(cs_nx[j]);
@@ -911,12 +913,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
           tc::mma_bf16_ts(d, ta_hi, db_lo, idesc, true);
           tc::mma_bf16_ts(d, ta_hi, db_hi, idesc, true);
         }
+        if (SM::BIG) tc::mma_commit(&mma_tile[mt]);   // the warps that own this tile's units start their exchange while the next tiles run
       }
-      tc::mma_commit(mma_done);
+      if (!SM::BIG) tc::mma_commit(mma_done);
       }
       __syncwarp();
     }
-    store_dg();   // HBM copies of dG (and the per-row dgin sums) overlap with the tensor-core step
+    if (!(p.dbg & 1)) store_dg();   // HBM copies of dG (and the per-row dgin sums) overlap with the tensor-core step
+    if constexpr (SM::BIG) {
+      // ---- warp w reads the accumulator of M tile w / 4, lane quarter w % 4: exactly the 32 units owned by CTA w of the
+      // cluster.  It stages that owner's slice [n][32 units] alone and sends it: no block barrier between the tensor
+      // core step and the exchange, and tile 0 is on its way while tiles 1..3 are still in the pipe.
+      const int mt = w >> 2, q = w & 3;
+      if (!*dead) {
+        if (!tc::mbar_wait(&mma_tile[mt], it & 1)) { *dead = 1; atomicExch(err, 4); }
+      }
+      if (!*dead) {
+        // single receive / staging buffers: phase `it` of ps_free completes when every CTA of the cluster has consumed
+        // the sums of this step, i.e. (a) all my copies of the previous step have landed and (b) every receive buffer
+        // may be overwritten by the copies issued below
+        if (!tc::mbar_wait(ps_free, it & 1)) { *dead = 1; atomicExch(err, 7); }
+      }
+      tc::fence_after_thread_sync();
+      __syncwarp();
+      float* pst_w = pstage + (size_t)w * NB * 32;
+#pragma unroll
+      for (int cb = 0; cb < RG; ++cb) {
+        float v[8];
+        tc::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB + cb * 8), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pst_w[(cb * 8 + i) * 32 + lane] = v[i];
+      }
+      tc::fence_before_thread_sync();
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (tc::elect_one()) {
+        const uint32_t d = w_u;
+        const uint32_t src = tc::smem_u32(pst_w);
+        const uint32_t dst_local = tc::smem_u32(ps + (size_t)rank * NB * 32);
+        if (p.xchg) {
+          // through L2 (profiles/r02_xchg_bench.txt): store my partials for owner d, wait for the writes, then a bulk
+          // load "multicast" to that single CTA: it lands at the same CTA-relative offset in d and completes d's mbarrier
+          unsigned char* g = p.xchg + ((((size_t)(blockIdx.x / C) * 2 + (it & 1)) * C + rank) * C + d) * (size_t)(NB * 128);
+          tc::bulk_store_s2g(g, src, slot_bytes);
+          tc::bulk_commit_wait_all();
+          tc::bulk_copy_g2s_multicast(dst_local, g, slot_bytes, tc::smem_u32(&ps_full[buf ^ 1]), (uint16_t)(1u << d));
+        } else {
+          tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, slot_bytes, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
+        }
+      }
+      __syncwarp();
+    } else {
     if (!*dead) {
       if (!tc::mbar_wait(mma_done, it & 1)) { *dead = 1; atomicExch(err, 4); }
     }
@@ -969,6 +1016,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
         tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, slot_bytes, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
       }
     }
+    }   // !BIG
 #pragma unroll
     for (int j = 0; j < NT; ++j) {   // rotate the pipeline registers
 #pragma unroll
@@ -1482,6 +1530,7 @@ int bwd_tc(const ScanBwdParams& p_in, cudaStream_t stream) {
   const Tiling t = pick_tiling<H>(p.B, lstm_scan_bwd_tc_kernel<H, 16>, TcBwdSmem<H, 16>::BYTES,
                                   lstm_scan_bwd_tc_kernel<H, 32>, TcBwdSmem<H, 32>::BYTES);
   p.rows_per_cluster = t.rows_per_cluster;
+  if (const char* e = getenv("R2D2_SCAN_DBG")) p.dbg = atoi(e);
   if constexpr (H == 512) {
     size_t cap = 0;
     unsigned char* scratch = scan_l2_exchange_enabled() ? scan_xchg_scratch(&cap) : nullptr;
