@@ -1,15 +1,17 @@
 #!/usr/bin/env python
-"""bench.py - learner sequence-steps/sec (batch x seq_len per learner iteration) of the B200-native
-learner hot path, BASELINE.json configs[1]: synthetic obs=17 act=6 hidden=256 seq_len=80 burn_in=40
-batch=256 per GPU (weak scaling: every rank owns a replay shard and a batch of 256; gradients are
-all-reduced over NCCL at the two optimiser steps).
+"""bench.py - learner sequence-steps/sec (batch x seq_len per learner iteration) of the B200-native learner hot
+path.  Headline workload = BASELINE.json configs[2], the largest single-GPU configuration: synthetic Humanoid
+shape obs=376 act=17 hidden=512 seq_len=80 burn_in=40 batch=512 PER GPU (weak scaling: every rank owns a replay
+shard in HBM and a batch of 512; the two flat gradient blocks are all-reduced over NCCL at the optimiser steps).
 
   python bench.py --gpus N --steps K --warmup W          # torchrun launches one process per GPU for N > 1
   python bench.py --impl reference ...                   # the reference's CPU implementation (oracle port)
+  python bench.py --config cfg2|cfg1                     # BASELINE.json configs[1] / configs[0] shapes
+  python bench.py --config replay                        # configs[3]: 250k stored sequence starts per GPU, sample / update
 
-A step = one pass of learner.py:84-139: prioritized sample from the HBM replay shard -> gather ->
-target/online chains -> TD/priority kernel -> critic BPTT + Adam -> actor chain -> DPG backward + Adam
--> priority write-back into the sum tree.  One JSON line on stdout (rank 0).
+A step = one pass of learner.py:84-139: prioritized sample from the HBM replay shard -> gather -> target/online
+chains -> TD/priority kernels -> critic BPTT + Adam -> actor chain -> DPG backward + Adam -> priority write-back into
+the sum tree.  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -31,12 +33,18 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 CONFIGS = {
-    # BASELINE.json configs[0] shapes (reference as-is, walker sizes) / configs[1] (headline) / configs[2]
+    # BASELINE.json configs[0] shapes (reference as-is, walker sizes) / configs[1] / configs[2] (headline)
     "cfg1": dict(obs=24, act=6, hidden=128, batch=32, burn_in=20, learning=40, n_step=5),
     "cfg2": dict(obs=17, act=6, hidden=256, batch=256, burn_in=40, learning=80, n_step=5),
     "cfg3": dict(obs=376, act=17, hidden=512, batch=512, burn_in=40, learning=80, n_step=5),
 }
 METRIC = "learner sequence-steps/sec (batch x seq_len)"
+DTYPE = "bf16x3 (fp32 operands split into bf16 hi+lo, three tensor-core passes, fp32 accumulate: ~16-bit operands)"
+
+
+def workload_string(name, c):
+    """identical in both arms (the driver compares them)"""
+    return f"{name}: " + " ".join(f"{k}={v}" for k, v in c.items())
 
 
 def lstm_flops_per_iteration(c):
@@ -96,19 +104,22 @@ class ClockSampler:
 
 
 def build_replay(engine, cfg, n_episodes, episode_len, seed, device):
+    """Per-GPU replay shard with synthetic episodes.  One episode's arrays are generated per 16 episodes (fresh
+    priorities every time): the content of a row does not change what a step costs."""
     rng = np.random.default_rng(seed)
     n_rows = episode_len + cfg.n_step
     rp = engine.DeviceReplay(cfg, capacity_rows=n_episodes * n_rows, device=device)
-    for _ in range(n_episodes):
-        term = np.zeros(n_rows, np.float32)
-        term[episode_len:] = 1
-        obs = rng.standard_normal((n_rows, cfg.obs), dtype=np.float32)
-        act = rng.uniform(-1, 1, (n_rows, cfg.act)).astype(np.float32)
-        rew = rng.standard_normal(n_rows, dtype=np.float32)
-        obs[episode_len:] = 0
-        act[episode_len:] = 0
-        rew[episode_len:] = 0
-        states = 0.1 * rng.standard_normal((episode_len, 4, 2, cfg.hidden), dtype=np.float32)
+    for e in range(n_episodes):
+        if e % 16 == 0:
+            term = np.zeros(n_rows, np.float32)
+            term[episode_len:] = 1
+            obs = rng.standard_normal((n_rows, cfg.obs), dtype=np.float32)
+            act = rng.uniform(-1, 1, (n_rows, cfg.act)).astype(np.float32)
+            rew = rng.standard_normal(n_rows, dtype=np.float32)
+            obs[episode_len:] = 0
+            act[episode_len:] = 0
+            rew[episode_len:] = 0
+            states = 0.1 * rng.standard_normal((episode_len, 4, 2, cfg.hidden), dtype=np.float32)
         prio = rng.uniform(0.01, 1.0, episode_len - (cfg.burn_in + cfg.learning)).astype(np.float32)
         rp.add_episode(obs, act, rew, term, states, prio)
     return rp
@@ -130,38 +141,56 @@ def cpu_model():
     return "unknown"
 
 
-def pick_cpu_threads(c):
-    """torch CPU ops of this size (batch x hidden LSTMCell steps) stop scaling - and can collapse - long
-    before a 100+ core box is full, so probe a few thread counts on a short LSTMCell fwd+bwd loop and keep
-    the fastest: the baseline gets the best setting this host offers, and `cores` reports it."""
+def pick_cpu_threads(name, c):
+    """Thread count of the CPU arms.  torch CPU ops of this size stop scaling - and can collapse - long before a
+    100+ core box is full, so FULL-BATCH port iterations (all phases: sample, chains, BPTT, Adam; a shortened window
+    so that a probe iteration costs ~1/10 of a real one) are timed for a few candidates and the fastest is kept.  The
+    choice is cached per (CPU model, core count, config) in /tmp so that `--impl reference` and the `cpu_baseline` leg
+    of the B200 arm, which run back to back on one box, use the same setting (round 1: a 12-step LSTMCell probe flipped
+    between 16 and 32 threads from run to run and moved the reference arm by 2.8x)."""
     ncpu = os.cpu_count() or 1
-    cands = sorted({t for t in (4, 8, 16, 32, 64, ncpu) if t <= ncpu})
-    cell = torch.nn.LSTMCell(c["hidden"], c["hidden"])
-    x = torch.randn(c["batch"], c["hidden"])
-    best, best_t = cands[0], float("inf")
+    key = f"{cpu_model()}|{ncpu}|{name}"
+    cache_path = "/tmp/r2d2_b200_cpu_threads.json"
+    try:
+        cache = json.load(open(cache_path))
+    except Exception:
+        cache = {}
+    if key in cache:
+        log(f"cpu threads: {cache[key]['threads']} (cached choice of this box: {cache[key]['probe']})")
+        return int(cache[key]["threads"])
+    from oracle import ref_port
+    cands = sorted({t for t in (8, 16, 32, 64) if t <= ncpu}) or [ncpu]
+    small = dict(c, burn_in=2, learning=6, n_step=2)
+    pc = ref_port.PathConfig(**small)
+    probe = {}
     for t in cands:
         torch.set_num_threads(t)
-        for rep in range(2):
+        lr = ref_port.PortLearner(pc, seed=1)
+        batch = ref_port.synthetic_batch(pc, seed=0)
+        ts = []
+        for rep in range(3):
             t0 = time.perf_counter()
-            h = cx = torch.zeros(c["batch"], c["hidden"])
-            for _ in range(12):
-                h, cx = cell(x, (h, cx))
-            h.sum().backward()
-            dt = time.perf_counter() - t0
-        log(f"cpu thread probe: {t} threads -> {dt * 1e3:.1f} ms")
-        if dt < best_t:
-            best, best_t = t, dt
-        elif dt > 2.0 * best_t:
-            break  # past the knee: more threads only add spin-wait contention (128 threads: 1800x slower here)
+            lr.iteration(batch, keep_tensors=False)
+            ts.append(time.perf_counter() - t0)
+        probe[t] = min(ts[1:])
+        log(f"cpu thread probe: {t} threads -> {probe[t] * 1e3:.0f} ms per shortened full-batch iteration")
+        if probe[t] > 2.0 * min(probe.values()):
+            break  # past the knee: more threads only add contention
+    best = min(probe, key=probe.get)
+    cache[key] = {"threads": best, "probe": {str(k): round(v, 4) for k, v in probe.items()}}
+    try:
+        json.dump(cache, open(cache_path, "w"))
+    except OSError:
+        pass
     return best
 
 
-def time_cpu_port(c, steps, warmup, threads=None, budget_s=150.0):
-    """The reference's CPU implementation of the path (oracle/ref_port.py: same torch CPU operators,
-    python loops, autograd, Adam, two-level WeightedRandomSampler draw) on this box's host cores.
+def time_cpu_port(name, c, steps, warmup, budget_s):
+    """The reference's CPU implementation of the path (oracle/ref_port.py: same torch CPU operators, python loops,
+    autograd, Adam, two-level WeightedRandomSampler draw) on this box's host cores, full batch, full window.
     Stops early (after >= 1 timed iteration) when `budget_s` of wall clock is spent."""
     from oracle import ref_port
-    threads = threads or pick_cpu_threads(c)
+    threads = pick_cpu_threads(name, c)
     torch.set_num_threads(threads)
     pc = ref_port.PathConfig(**c)
     lr = ref_port.PortLearner(pc, seed=1)
@@ -177,26 +206,28 @@ def time_cpu_port(c, steps, warmup, threads=None, budget_s=150.0):
         log(f"cpu port iteration {i}: {time.perf_counter() - t0:.2f} s")
         if times and time.perf_counter() - t_start > budget_s:
             break
-    sec = float(np.mean(times))
+    sec = float(np.median(times))
     return c["batch"] * c["learning"] / sec, sec, threads, len(times)
 
 
-def run_reference(args, c):
+def run_reference(args, name, c):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, sec, threads, done = time_cpu_port(c, args.steps, args.warmup, budget_s=240.0)
+    warm = 1   # a CPU iteration takes seconds: one untimed iteration warms allocator and thread pool
+    value, sec, threads, done = time_cpu_port(name, c, args.steps, warm, budget_s=200.0)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "seq-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "steps_timed": done, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: " + " ".join(f"{k}={v}" for k, v in c.items()),
+            "steps": args.steps, "steps_timed": done, "warmup": args.warmup, "warmup_run": warm,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_string(name, c),
                        "note": "reference CPU learner (oracle/ref_port.py port; /root/reference is python and not "
-                               "present on this box), full batch per step; a step is one full learner iteration "
-                               "(~1-2 s on the host): at most 240 s of them are timed (steps_timed), the rate does "
-                               "not depend on the count"},
+                               "present on this box), full batch and full window per step; a step is one learner "
+                               "iteration (seconds on the host): at most 200 s of them are timed (steps_timed, median), "
+                               "the rate does not depend on the count"},
             "cpu_baseline": {"value": value, "unit": "seq-steps/s", "cores": threads, "kind": "port",
-                             "sample": f"{done} full learner iterations at batch {c['batch']} after {args.warmup} warm-up, "
-                                       f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)",
+                             "sample": f"{done} full learner iterations at batch {c['batch']} after {warm} warm-up, "
+                                       f"{threads} torch threads (fastest of a full-batch probe over {os.cpu_count()} host cores)",
                              "cpu_model": cpu_model(), "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": "seq-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -225,212 +256,397 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+class Arm:
+    """engine + replay shard of one configuration, and the two timed loops (HBM-resident and host-fed)."""
+
+    def __init__(self, engine_mod, c, dev, rank, episodes, data_parallel, seed_base=100):
+        self.engine_mod, self.c, self.dev = engine_mod, c, dev
+        self.cfg = engine_mod.PathConfig(**c)
+        self.eng = engine_mod.LearnerEngine(self.cfg, device=dev, seed=1)
+        if data_parallel:
+            self.eng.enable_data_parallel()
+        self.ep_len = 250
+        self.episodes = episodes
+        self.rp = build_replay(engine_mod, self.cfg, episodes, self.ep_len, seed=seed_base + rank, device=dev)
+        self.gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def step_resident(self):
+        self.rp.sample_into(self.eng, generator=self.gen)
+        self.eng.step()
+        self.rp.update_priorities(self.eng.leaf_idx, self.eng.priority)
+
+    def time_resident(self, steps, warmup, barrier, clocks=None):
+        for _ in range(warmup):
+            self.step_resident()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if clocks is not None:
+            clocks.mark(True)
+        ev0.record()
+        for _ in range(steps):
+            self.step_resident()
+        ev1.record()
+        barrier()
+        if clocks is not None:
+            clocks.mark(False)
+        return ev0.elapsed_time(ev1) / steps
+
+    def time_host_fed(self, steps, warmup, barrier):
+        """e2e: the whole iteration - sum-tree draw + gather, learner phases, tree write-back - with the step's batch
+        ALSO arriving from pinned HOST memory (the reference's boundary: replay_memory.py:123-133 builds the batch on
+        the host and copies it to the device every iteration) and the priorities / losses read back to the host with
+        a stream synchronisation (learner.py:135).  The host batch overwrites the device-gathered one, so the timed
+        region contains both the device sampler work and the host->device traffic of the same bytes."""
+        eng, rp = self.eng, self.rp
+        B = self.cfg.batch
+        n_pool = 3
+        pool = []
+        for _ in range(n_pool):
+            rp.sample_into(eng, generator=self.gen)
+            torch.cuda.synchronize()
+            pool.append({k: getattr(eng, k).cpu().pin_memory() for k in ("obs", "act", "rew", "term", "states")})
+        host_prio = torch.empty(B, dtype=torch.float32).pin_memory()
+        host_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * 4 for v in pool[0].values())
+        d2h = (B + 2) * 4
+        keys = list(pool[0].keys())
+        copy_stream = torch.cuda.Stream()
+        stage = [{k: torch.empty_like(getattr(eng, k)) for k in keys} for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        for e in consumed:
+            e.record(torch.cuda.current_stream())
+
+        def prefetch(i):     # pinned batch of step i crosses PCIe on a copy stream while step i-1 computes
+            s_ = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[s_])
+                for k, v in pool[i % n_pool].items():
+                    stage[s_][k].copy_(v, non_blocking=True)
+                ready[s_].record(copy_stream)
+
+        def step_host(i):
+            s_ = i % 2
+            cur = torch.cuda.current_stream()
+            rp.sample_into(eng, generator=self.gen)               # sum-tree draw + gather (device sampler, learner.py:84)
+            cur.wait_event(ready[s_])
+            for k in keys:                                        # the host-built batch of this step (H2D done on the copy stream)
+                getattr(eng, k).copy_(stage[s_][k], non_blocking=True)
+            consumed[s_].record(cur)
+            prefetch(i + 1)
+            eng.step()
+            rp.update_priorities(eng.leaf_idx, eng.priority)      # learner.py:136-139
+            host_prio.copy_(eng.priority, non_blocking=True)
+            host_loss.copy_(eng.losses, non_blocking=True)
+            cur.synchronize()                                     # the host consumes the priorities every iteration
+
+        prefetch(0)
+        for i in range(warmup):
+            step_host(i)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(warmup, warmup + steps):
+            step_host(i)
+        ev1.record()
+        barrier()
+        copy_stream.synchronize()
+        return ev0.elapsed_time(ev1) / steps, h2d, d2h
+
+    @property
+    def launches_per_step(self):
+        return self.eng.launches_per_iteration + 2 + 1   # + tree_sample, gather_batch + tree_update
+
+    def close(self):
+        self.rp.close()
+        self.eng.close()
+
+
+def scan_roofline(nv, c, dev, peaks, ms_iter):
+    """Roofline of the dominant kernel: the persistent LSTM scan (the serial h*W_hh^T half of every cell step;
+    the hoisted x*W_ih^T half runs in gemm_f32).  Algorithmic FLOPs per launch = 2*B*H*4H per cell step x S steps.
+    Forward and BPTT kernels are timed alone with CUDA events on the launch stream."""
+    B, H = c["batch"], c["hidden"]
+    S = c["burn_in"] + c["n_step"] + c["learning"]
+    gin = torch.randn(S, B, 4 * H, device=dev) * 0.5
+    whh = (torch.rand(4 * H, H, device=dev) * 2 - 1) / np.sqrt(4 * H)
+    gates = torch.empty_like(gin)
+    hs = torch.empty(S + 1, B, H, device=dev)
+    cs = torch.empty(S + 1, B, H, device=dev)
+    dh = torch.randn(S, B, H, device=dev) * 0.01
+    lib, st = nv.lib(), nv.current_stream()
+    scratch = torch.empty(B * 4 * H + 64, device=dev)
+
+    def fwd():
+        nv.check(lib.r2d2_lstm_scan_forward(nv.dptr(gin), nv.dptr(whh), None, None, nv.dptr(gates), nv.dptr(hs),
+                                            nv.dptr(cs), None, S, B, H, 1, nv.dptr(scratch), st))
+
+    def bwd():
+        nv.check(lib.r2d2_lstm_scan_backward(nv.dptr(gates), nv.dptr(hs), nv.dptr(cs), nv.dptr(whh), nv.dptr(dh), 0,
+                                             nv.dptr(gates), nv.dptr(gates), S, B, H, 1, nv.dptr(scratch), st))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        reps = 5
+        ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        out[name] = ev0.elapsed_time(ev1) / reps
+    scan_flops = 2.0 * B * H * 4 * H * S
+    achieved = scan_flops / (out["fwd"] * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r02_scan_fwd_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    kname = ("lstm_scan_fwd_big_kernel (H=512: cluster of 16, 7 resident clusters x <=80 rows as two ping-pong sub-tiles, "
+             "W_hh in TMEM + smem tail, h_t all-gather through L2 multicast)") if H == 512 else \
+        "lstm_scan_fwd_pp_kernel (persistent cluster LSTM scan, tcgen05 ping-pong over two row sub-tiles, W_hh in TMEM)"
+    flops_it = lstm_flops_per_iteration(c)
+    return {"kernel": kname + f", {S} cell steps", "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
+            "traffic_source": "profiles/r02_scan_fwd_traffic.json (ncu --set full of this kernel, dram read + write per launch)"
+            if traffic else None,
+            "peak_source": peaks["source"] + " bf16 dense burst (kernel timed alone)",
+            "us_per_step": out["fwd"] * 1e3 / S,
+            "bptt_kernel": {"us_per_step": out["bwd"] * 1e3 / S,
+                            "achieved_tflops": scan_flops / (out["bwd"] * 1e-3) / 1e12,
+                            "frac": scan_flops / (out["bwd"] * 1e-3) / 1e12 / peaks["bf16_burst"]},
+            "whole_iteration": {"lstm_flops": flops_it, "achieved_tflops": flops_it / (ms_iter * 1e-3) / 1e12,
+                                "frac_of_sustained_peak": flops_it / (ms_iter * 1e-3) / 1e12 / peaks["bf16_sustained"]}}
+
+
+def run_replay_bench(args, engine, dev, world, rank, dist, barrier):
+    """BASELINE.json configs[3]: GPU-resident prioritized replay, 2 M stored sequence starts sharded 8-way = 250 k starts
+    per GPU (1000 episodes x 250 starts, Humanoid row widths): sum-tree sample + gather and priority-update throughput,
+    index bit-exactness against the C restatement of the tree (oracle/sumtree_oracle.c) - checker only."""
+    from oracle.sumtree import SumTreeOracle
+    c = CONFIGS["cfg3"]
+    cfg = engine.PathConfig(**c)
+    n_ep, starts = 1000, 250
+    E = starts + cfg.burn_in + cfg.learning
+    n_rows = E + cfg.n_step
+    rp = engine.DeviceReplay(cfg, capacity_rows=n_ep * n_rows, device=dev)
+    oracle = SumTreeOracle(n_ep * n_rows) if rank == 0 else None
+    rng = np.random.default_rng(rank)
+    t0 = time.time()
+    obs = rng.standard_normal((n_rows, cfg.obs), dtype=np.float32)
+    act = rng.uniform(-1, 1, (n_rows, cfg.act)).astype(np.float32)
+    rew = rng.standard_normal(n_rows, dtype=np.float32)
+    term = np.zeros(n_rows, np.float32)
+    term[E:] = 1
+    st = 0.1 * rng.standard_normal((E, 4, 2, cfg.hidden), dtype=np.float32)
+    for e in range(n_ep):
+        p = rng.uniform(0.01, 1.0, starts).astype(np.float32)
+        rp.add_episode(obs, act, rew, term, st, p)
+        if oracle is not None:
+            oracle.set_range(e * n_rows, p)
+    torch.cuda.synchronize()
+    ingest_s = time.time() - t0
+    eng = engine.LearnerEngine(cfg, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    B = cfg.batch
+    steps, warm = max(args.steps, 50), max(args.warmup, 5)
+    for _ in range(warm):
+        rp.sample_into(eng, generator=gen)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        rp.sample_into(eng, generator=gen)
+    ev1.record()
+    barrier()
+    ms_sample = ev0.elapsed_time(ev1) / steps
+    u = torch.rand(1 << 20, device=dev, generator=gen)
+    for _ in range(3):
+        leaf = rp.sample_indices(u)
+    ev0.record()
+    for _ in range(10):
+        leaf = rp.sample_indices(u)
+    ev1.record()
+    torch.cuda.synchronize()
+    draws_per_s = 10 * u.numel() / (ev0.elapsed_time(ev1) * 1e-3)
+    exact = exact_after = None
+    if rank == 0:   # same uniforms, same tree: identical flat indices from the CUDA tree and its C restatement
+        exact = bool(np.array_equal(leaf.cpu().numpy(), oracle.sample(u.cpu().numpy())))
+    prio = torch.rand(B, device=dev)
+    for _ in range(warm):
+        rp.update_priorities(eng.leaf_idx, prio)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        rp.update_priorities(eng.leaf_idx, prio)
+    ev1.record()
+    barrier()
+    ms_update = ev0.elapsed_time(ev1) / steps
+    if rank == 0:   # and again after a batch of priority writes (duplicates: last writer wins in both)
+        oracle.update_batch(eng.leaf_idx.cpu().numpy(), prio.cpu().numpy())
+        u2 = torch.rand(100000, device=dev, generator=gen)
+        exact_after = bool(np.array_equal(rp.sample_indices(u2).cpu().numpy(), oracle.sample(u2.cpu().numpy())))
+    t = torch.tensor([ms_sample, ms_update], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_sample, ms_update = float(t[0]), float(t[1])
+    batch_bytes = 4 * (cfg.rows * B * (cfg.obs + cfg.act + 2) + 8 * B * cfg.hidden)
+    peaks = measured_peaks()
+    if rank == 0:
+        emit({"metric": "replay sampled sequences/sec (sum-tree draw + time-major gather)", "value": world * B / (ms_sample * 1e-3),
+              "unit": "sequences/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_sample,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 data, fp32 tree sums, int64 indices",
+              "data": "synthetic",
+              "config": {"workload": f"replay: {n_ep * starts} stored sequence starts per GPU ({n_ep} episodes x {n_rows} rows, "
+                                     f"obs={cfg.obs} act={cfg.act} hidden={cfg.hidden}), batch {B} x {cfg.rows} rows per draw",
+                         "total_starts": world * n_ep * starts},
+              "updates_per_s": world * B / (ms_update * 1e-3), "update_us_per_batch": ms_update * 1e3,
+              "sample_gather_us_per_batch": ms_sample * 1e3, "tree_draws_per_s_rank0": draws_per_s,
+              "indices_bit_exact_vs_c_tree": exact, "indices_bit_exact_after_update": exact_after,
+              "ingest_s_per_shard": round(ingest_s, 2),
+              "roofline": {"kernel": "gather_batch_kernel (+ tree_sample_kernel)", "bound": "hbm",
+                           "achieved": 2 * batch_bytes / (ms_sample * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                           "frac": 2 * batch_bytes / (ms_sample * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                           "algorithmic_bytes": 2 * batch_bytes, "peak_source": peaks["source"] + " copy bandwidth"},
+              "gpu_launches": 3 * steps})
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS) + ["replay"])
     ap.add_argument("--episodes", type=int, default=384, help="episodes in the per-GPU replay shard")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs / strong-scaling legs (profiling runs)")
+    ap.add_argument("--cpu-steps", type=int, default=4)
     args = ap.parse_args()
-    c = CONFIGS[args.config]
     if args.warmup < 3:
         args.warmup = 3
+    name = args.config if args.config != "replay" else "cfg3"
+    c = CONFIGS[name]
     if args.impl == "reference":
-        return run_reference(args, c)
+        return run_reference(args, name, c)
 
     from r2d2_b200 import engine, native as nv
+    from r2d2_b200.dist_env import DistEnv
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    env = DistEnv.from_environ()
+    world, rank, local = env.world, env.rank, env.local_rank
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     dist = None
     if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: keep NCCL's banner / debug output out of it
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_bench_%h_%p.log")
-        dist.init_process_group("nccl", device_id=dev)
-    log(f"world={world} rank={rank}: building engine + replay shard")
-    cfg = engine.PathConfig(**c)
-    eng = engine.LearnerEngine(cfg, device=dev, seed=1)
-    eng.enable_data_parallel()
-    ep_len = 250
-    rp = build_replay(engine, cfg, args.episodes, ep_len, seed=100 + rank, device=dev)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    B, L, T, O, A, H = cfg.batch, cfg.learning, cfg.rows, cfg.obs, cfg.act, cfg.hidden
-
-    def step_resident():
-        rp.sample_into(eng, generator=gen)
-        eng.step()
-        rp.update_priorities(eng.leaf_idx, eng.priority)
+        dist = env.init_process_group("nccl", device=dev)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    log("warm-up (HBM-resident arm)")
+    if args.config == "replay":
+        run_replay_bench(args, engine, dev, world, rank, dist, barrier)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    log(f"world={world} rank={rank}: building engine + replay shard ({name})")
+    arm = Arm(engine, c, dev, rank, args.episodes, data_parallel=True)
+    cfg = arm.cfg
+    B, L = cfg.batch, cfg.learning
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()          # started before the warm-up so that samples exist when the timed region begins
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    clocks.mark(True)
-    ev0.record()
-    for _ in range(args.steps):
-        step_resident()
-    ev1.record()
-    barrier()
-    clocks.mark(False)
-    ms = ev0.elapsed_time(ev1) / args.steps
+    log("HBM-resident arm")
+    ms = arm.time_resident(args.steps, args.warmup, barrier, clocks)
     clk = clocks.stop() if rank == 0 else None
-    t_ms = torch.tensor([ms], device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = max_over_ranks(ms)
     value = world * B * L / (ms * 1e-3)
-    launches_per_step = eng.launches_per_iteration + 6 + 1   # + sample/gather kernels + tree update
+    log(f"resident arm: {ms:.3f} ms/step; host-fed (e2e) arm")
+    ms_e2e, h2d, d2h = arm.time_host_fed(args.steps, args.warmup, barrier)
+    ms_e2e = max_over_ranks(ms_e2e)
+    e2e_value = world * B * L / (ms_e2e * 1e-3)
+    replicas_identical = arm.eng.replicas_identical() if world > 1 else None
+    launches_per_step = arm.launches_per_step
 
-    log(f"resident arm: {ms:.3f} ms/step; e2e arm")
-    # ---- e2e: the same iteration fed from HOST buffers (the reference's boundary: replay_memory.py:123-133
-    # copies the sampled batch to the device each iteration, learner.py:135 reads the TD result back)
-    n_pool = 4
-    pool = []
-    for i in range(n_pool):
-        rp.sample_into(eng, generator=gen)
-        torch.cuda.synchronize()
-        pool.append({k: getattr(eng, k).cpu().pin_memory() for k in ("obs", "act", "rew", "term", "states")})
-    host_prio = torch.empty(B, dtype=torch.float32).pin_memory()
-    host_loss = torch.empty(2, dtype=torch.float32).pin_memory()
-    h2d = sum(v.numel() * 4 for v in pool[0].values())
-    d2h = (B + 2) * 4
-
-    # Double-buffered feed: the pinned batch of step i+1 crosses PCIe on a copy stream while step i computes; the
-    # compute stream only does a device-to-device move of the staged batch (5 MB at HBM speed) before each step.
-    keys = list(pool[0].keys())
-    copy_stream = torch.cuda.Stream()
-    stage = [{k: torch.empty_like(getattr(eng, k)) for k in keys} for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    for e in consumed:
-        e.record(torch.cuda.current_stream())
-
-    def prefetch(i):
-        s_ = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[s_])          # the staged batch of step i-2 has been moved out
-            for k, v in pool[i % n_pool].items():
-                stage[s_][k].copy_(v, non_blocking=True)
-            ready[s_].record(copy_stream)
-
-    def step_host(i):
-        s_ = i % 2
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ready[s_])
-        for k in keys:
-            getattr(eng, k).copy_(stage[s_][k], non_blocking=True)
-        consumed[s_].record(cur)
-        prefetch(i + 1)                                   # H2D of the next step's inputs, overlapped with this step
-        eng.step()
-        host_prio.copy_(eng.priority, non_blocking=True)
-        host_loss.copy_(eng.losses, non_blocking=True)
-        cur.synchronize()                                 # the host consumes the priorities every iteration
-
-    prefetch(0)
-    for i in range(args.warmup):
-        step_host(i)
-    barrier()
-    ev0.record()
-    for i in range(args.warmup, args.warmup + args.steps):
-        step_host(i)
-    ev1.record()
-    barrier()
-    copy_stream.synchronize()
-    ms_e2e = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
-    if dist is not None:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * L / (float(ms_e2e.item()) * 1e-3)
-
-    log("roofline: timing the scan kernel alone")
-    # ---- roofline of the dominant kernel: the persistent LSTM scan (serial half of every cell step).
-    # algorithmic FLOPs per launch = 2 * B * H * 4H per cell step x S steps (F_cell = 16 B H^2 covers
-    # both halves; the hoisted x*W_ih half runs in gemm_f32).  Timed alone with CUDA events on the launch stream.
+    log("roofline: timing the scan kernels alone")
     peaks = measured_peaks()
-    S = cfg.burn_in + cfg.n_step + cfg.learning
-    gin = torch.randn(S, B, 4 * H, device=dev) * 0.5
-    whh = (torch.rand(4 * H, H, device=dev) * 2 - 1) / np.sqrt(4 * H)
-    gates = torch.empty_like(gin)
-    hs = torch.empty(S + 1, B, H, device=dev)
-    cs = torch.empty(S + 1, B, H, device=dev)
-    lib, st = nv.lib(), nv.current_stream()
-    scratch = torch.empty(B * 4 * H, device=dev)
+    roofline = scan_roofline(nv, c, dev, peaks, ms)
 
-    def scan():
-        nv.check(lib.r2d2_lstm_scan_forward(nv.dptr(gin), nv.dptr(whh), None, None, nv.dptr(gates), nv.dptr(hs),
-                                            nv.dptr(cs), None, S, B, H, 1, nv.dptr(scratch), st))
-    for _ in range(3):
-        scan()
-    torch.cuda.synchronize()
-    reps = 10
-    ev0.record()
-    for _ in range(reps):
-        scan()
-    ev1.record()
-    torch.cuda.synchronize()
-    scan_ms = ev0.elapsed_time(ev1) / reps
-    scan_flops = 2.0 * B * H * 4 * H * S
-    achieved = scan_flops / (scan_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "scan_fwd_traffic.json")
-    if os.path.isfile(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"kernel": "lstm_scan_fwd_pp_kernel (persistent cluster LSTM scan, tcgen05 ping-pong over two row sub-tiles, W_hh in TMEM, %d cell steps)" % S, "bound": "tensor",
-                "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
-                "traffic": traffic, "peak_source": peaks["source"] + " bf16 dense burst (kernel timed alone)",
-                "us_per_step": scan_ms * 1e3 / S,
-                "whole_iteration": {"lstm_flops": lstm_flops_per_iteration(c),
-                                    "achieved_tflops": lstm_flops_per_iteration(c) / (ms * 1e-3) / 1e12,
-                                    "frac_of_sustained_peak": lstm_flops_per_iteration(c) / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"]}}
+    # ---- strong scaling (SURVEY 8e): the configuration's batch is the GLOBAL batch, B/N sequences per GPU
+    strong = None
+    if world > 1 and not args.no_extras and B % world == 0:
+        log("strong-scaling leg")
+        cs = dict(c, batch=B // world)
+        arm_s = Arm(engine, cs, dev, rank, max(64, args.episodes // world), data_parallel=True, seed_base=500)
+        ms_s = max_over_ranks(arm_s.time_resident(max(20, args.steps // 2), args.warmup, barrier))
+        strong = {"global_batch": B, "per_gpu_batch": B // world, "ms_per_step": ms_s,
+                  "value": B * L / (ms_s * 1e-3), "unit": "seq-steps/s",
+                  "replicas_identical": arm_s.eng.replicas_identical()}
+        arm_s.close()
+    # ---- the other BASELINE configs on the same build (per GPU batch as configured; same timed loop, fewer steps)
+    others = {}
+    if not args.no_extras:
+        for oname in ("cfg2", "cfg1"):
+            if oname == name:
+                continue
+            log(f"secondary config {oname}")
+            arm_o = Arm(engine, CONFIGS[oname], dev, rank, 128, data_parallel=True, seed_base=900)
+            ms_o = max_over_ranks(arm_o.time_resident(50, 5, barrier))
+            co = CONFIGS[oname]
+            others[oname] = {"workload": workload_string(oname, co), "ms_per_step": ms_o,
+                             "value": world * co["batch"] * co["learning"] / (ms_o * 1e-3), "unit": "seq-steps/s",
+                             "gpu_launches_per_step": arm_o.launches_per_step}
+            arm_o.close()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         log("cpu_baseline leg (oracle port on host cores)")
-        v, sec, threads, done = time_cpu_port(c, args.cpu_steps, 1, budget_s=60.0)
+        v, sec, threads, done = time_cpu_port(name, c, args.cpu_steps, 1, budget_s=45.0)
         cpu_baseline = {"value": v, "unit": "seq-steps/s", "cores": threads, "kind": "port",
-                        "sample": f"{done} full learner iterations at batch {B} after 1 warm-up ({sec:.2f} s each), "
-                                  f"{threads} torch threads (best of a probe over {os.cpu_count()} host cores)",
+                        "sample": f"{done} full learner iterations at batch {B} after 1 warm-up ({sec:.2f} s each, median), "
+                                  f"{threads} torch threads (fastest of a full-batch probe over {os.cpu_count()} host cores; "
+                                  f"same choice as --impl reference on this box)",
                         "cpu_model": cpu_model(), "host_cores": os.cpu_count()}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "seq-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32 (bf16x3 split tensor-core MMAs, fp32 accumulate)", "data": "synthetic",
-                "config": {"workload": f"{args.config}: " + " ".join(f"{k}={v}" for k, v in c.items()) + " per GPU",
+                "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+                "config": {"workload": workload_string(name, c), "per_gpu": True,
                            "parallelism": f"dp{world}", "global_batch": world * B,
-                           "replay_shard": f"{args.episodes} episodes x {ep_len + cfg.n_step} rows per GPU in HBM",
-                           "l2": "inputs larger than L2: every step streams >1 GB of activations and gathers its batch "
+                           "replay_shard": f"{args.episodes} episodes x {arm.ep_len + cfg.n_step} rows per GPU in HBM",
+                           "l2": "inputs larger than L2: every step streams several GB of activations and gathers its batch "
                                  "from a multi-GB replay shard"},
-                "e2e": {"value": e2e_value, "unit": "seq-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "feed": "pinned host batch -> staging buffer on a copy stream (step i+1 overlaps step i), "
-                                "priorities + losses read back and the stream synchronised every step"},
+                "e2e": {"value": e2e_value, "unit": "seq-steps/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h,
+                        "feed": "per step: sum-tree draw + gather on the device, the step's batch copied from PINNED HOST memory "
+                                "(copy stream, overlaps the previous step) over the gathered one, learner iteration, tree "
+                                "write-back, priorities + losses read back to the host and the stream synchronised"},
                 "iterations_per_s": world * 1e3 / ms, "rows_per_s": world * B * (cfg.burn_in + L) / (ms * 1e-3),
-                "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "clocks": clk}
+                "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clk,
+                "replicas_identical": replicas_identical, "strong_scaling": strong, "other_configs": others}
         emit(line)
+    arm.close()
     if dist is not None:
         dist.destroy_process_group()
 

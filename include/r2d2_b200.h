@@ -209,7 +209,11 @@ int r2d2_learner_destroy(r2d2_learner_t* l);
 int r2d2_learner_buffers_get(r2d2_learner_t* l, r2d2_learner_buffers* out);
 /* phase 1: target chains, online critic chain, TD/priority kernel, critic BPTT -> critic_grads */
 int r2d2_learner_critic_phase(r2d2_learner_t* l, r2d2_stream_t stream);
-/* phase 2: critic Adam (grads * grad_scale), actor chain (zero state, 2 cell steps/row), critic on
+/* optional, between phase 1 and phase 2: the actor's forward chain of the DPG update (learner.py:117,120-123; zero
+ * state, 2 cell steps per row).  It does not read the critic, so a data-parallel caller issues it while the
+ * all-reduce of critic_grads is in flight; phase 2 then skips it.  Without this call phase 2 runs it itself. */
+int r2d2_learner_actor_forward(r2d2_learner_t* l, r2d2_stream_t stream);
+/* phase 2: critic Adam (grads * grad_scale), actor chain unless r2d2_learner_actor_forward already ran, critic on
  * actor actions, dgrad through critic, actor BPTT -> actor_grads */
 int r2d2_learner_actor_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t stream);
 /* phase 3: actor Adam, step counter, hard target update every target_update_interval steps */

@@ -194,6 +194,10 @@ int r2d2_learner_critic_phase(r2d2_learner_t* l, r2d2_stream_t stream) {
   R2D2_REQUIRE(l, "null");
   return learner_critic_phase(reinterpret_cast<Learner*>(l), S(stream));
 }
+int r2d2_learner_actor_forward(r2d2_learner_t* l, r2d2_stream_t stream) {
+  R2D2_REQUIRE(l, "null");
+  return learner_actor_forward(reinterpret_cast<Learner*>(l), S(stream));
+}
 int r2d2_learner_actor_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t stream) {
   R2D2_REQUIRE(l, "null");
   return learner_actor_phase(reinterpret_cast<Learner*>(l), grad_scale, S(stream));

@@ -12,10 +12,10 @@ __device__ __forceinline__ float value_rescale(float x) {
   return x > 0.f ? m : (x < 0.f ? -m : 0.f);
 }
 
-// grid: ceil(B/32) CTAs, 1024 threads = 32 warps; lane -> batch column, warp -> time rows i = w, w+32, ...
+// fallback (no td_sq buffer to reduce through): grid ceil(B/32) CTAs, 1024 threads = 32 warps; lane -> batch column, warp -> time rows i = w, w+32, ...
 // (the kernel moves ~1 MB: it is bound by the length of the per-thread dependent load chain, hence the wide block)
 constexpr int TD_WARPS = 32;
-__global__ void __launch_bounds__(TD_WARPS * 32) td_priority_kernel(TdPriorityParams p) {
+__global__ void __launch_bounds__(TD_WARPS * 32) td_priority_column_kernel(TdPriorityParams p) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = blockIdx.x * 32 + lane;
   const int L = p.L, B = p.B, A = p.A;
@@ -64,6 +64,80 @@ __global__ void __launch_bounds__(TD_WARPS * 32) td_priority_kernel(TdPriorityPa
       for (int k = 0; k < TD_WARPS; ++k) tot += s_sq[k];
       atomicAdd(p.loss_sum, tot / ((float)L * (float)B * (float)A));
     }
+  }
+}
+
+// ---- the path's TD kernel pair (learner.py:107-111,135-138): every global access is a lane-contiguous 128-byte line.
+// Pass 1, one warp per (time row i, 32 consecutive batch elements): the [32 x A] spans of q and q_next are ONE contiguous
+// run of 32*A floats each (layout [L][B][A]); the warp copies them into shared memory with unit-stride loads, every lane
+// then owns one batch element (A values, stride-A shared reads: conflict free for odd A, 2-way for A = 6), writes the
+// target and the loss gradient back into the same shared slots and the warp stores them with unit-stride writes.
+// Pass 2 reduces td_sq[L,B] per batch element (max / mean with the [b:-1:B] quirk) and sums the loss: lanes along b.
+constexpr int TD1_WARPS = 8;
+__global__ void __launch_bounds__(TD1_WARPS * 32) td_elem_kernel(TdPriorityParams p) {
+  extern __shared__ float td_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int L = p.L, B = p.B, A = p.A;
+  const int i = blockIdx.y * TD1_WARPS + w;
+  const int b0 = blockIdx.x * 32;
+  if (i >= L) return;
+  const int nb = min(32, B - b0), span = nb * A;
+  float* sq_ = td_smem + (size_t)w * 2 * 32 * A;       // q, then (in place) dq
+  float* sn_ = sq_ + 32 * A;                           // q_next, then (in place) target
+  const size_t base = ((size_t)i * B + b0) * A;
+  for (int k = lane; k < span; k += 32) {
+    sq_[k] = __ldg(p.q + base + k);
+    sn_[k] = __ldg(p.q_next + base + k);
+  }
+  __syncwarp();
+  const float grad_scale = 2.0f / ((float)L * (float)B * (float)A);
+  if (lane < nb) {
+    const int b = b0 + lane;
+    const float r = __ldg(p.rew + (size_t)(p.burn_in + i) * B + b);
+    const float d = __ldg(p.term + (size_t)(p.burn_in + i + p.n_step - 1) * B + b);
+    const float cont = p.gamma_n * (1.0f - d);
+    float sq = 0.f;
+    for (int a = 0; a < A; ++a) {
+      const float y = value_rescale(r + cont * sn_[lane * A + a]);
+      const float diff = sq_[lane * A + a] - y;
+      sn_[lane * A + a] = y;
+      sq_[lane * A + a] = grad_scale * diff;
+      sq += diff * diff;
+    }
+    p.td_sq[(size_t)i * B + b] = sq / (float)A;
+  }
+  __syncwarp();
+  if (p.target) for (int k = lane; k < span; k += 32) p.target[base + k] = sn_[k];
+  if (p.dq) for (int k = lane; k < span; k += 32) p.dq[base + k] = sq_[k];
+}
+
+constexpr int TD2_WARPS = 8;
+__global__ void __launch_bounds__(TD2_WARPS * 32) td_reduce_kernel(TdPriorityParams p) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  const int L = p.L, B = p.B;
+  float run_max = -INFINITY, run_sum = 0.f, tot = 0.f;
+  if (b < B) {
+    for (int i = w; i < L; i += TD2_WARPS) {
+      const float td = p.td_sq[(size_t)i * B + b];
+      tot += td;
+      // learner.py:137 `average_td_loss[b:-1:B]` drops flat index L*B-1, i.e. (i=L-1, b=B-1)
+      if (!(i == L - 1 && b == B - 1)) { run_max = fmaxf(run_max, td); run_sum += td; }
+    }
+  }
+  __shared__ float s_max[TD2_WARPS][32], s_sum[TD2_WARPS][32], s_tot[TD2_WARPS][32];
+  s_max[w][lane] = run_max; s_sum[w][lane] = run_sum; s_tot[w][lane] = tot;
+  __syncthreads();
+  if (w == 0) {
+    float mx = s_max[0][lane], sm = s_sum[0][lane], tt = s_tot[0][lane];
+#pragma unroll
+    for (int k = 1; k < TD2_WARPS; ++k) { mx = fmaxf(mx, s_max[k][lane]); sm += s_sum[k][lane]; tt += s_tot[k][lane]; }
+    if (b < B && p.priority) {
+      const int count = L - ((b == B - 1) ? 1 : 0);
+      p.priority[b] = p.eta * mx + (1.0f - p.eta) * (sm / (float)count);  // utils.py:17-18
+    }
+    tt = warp_sum(tt);   // critic loss = mean over (i, b, a) of diff^2 = sum of td_sq / (L * B)
+    if (lane == 0 && p.loss_sum) atomicAdd(p.loss_sum, tt / ((float)L * (float)B));
   }
 }
 
@@ -159,8 +233,18 @@ int td_priority(const TdPriorityParams& p, cudaStream_t stream) {
   R2D2_REQUIRE(p.q && p.q_next && p.rew && p.term, "null input");
   R2D2_REQUIRE(p.L > 0 && p.B > 0 && p.A > 0, "shape");
   if (p.loss_sum) R2D2_CUDA_TRY(cudaMemsetAsync(p.loss_sum, 0, sizeof(float), stream));
-  td_priority_kernel<<<ceil_div(p.B, 32), TD_WARPS * 32, 0, stream>>>(p);
-  count_launch();
+  const size_t smem = (size_t)TD1_WARPS * 2 * 32 * p.A * sizeof(float);
+  if (p.td_sq && smem <= 48 * 1024) {   // the path's configuration: two line-coalesced passes over L x B x A and L x B
+    td_elem_kernel<<<dim3(ceil_div(p.B, 32), ceil_div(p.L, TD1_WARPS)), TD1_WARPS * 32, smem, stream>>>(p);
+    count_launch();
+    if (p.priority || p.loss_sum) {
+      td_reduce_kernel<<<ceil_div(p.B, 32), TD2_WARPS * 32, 0, stream>>>(p);
+      count_launch();
+    }
+  } else {
+    td_priority_column_kernel<<<ceil_div(p.B, 32), TD_WARPS * 32, 0, stream>>>(p);
+    count_launch();
+  }
   R2D2_CUDA_TRY(cudaGetLastError());
   return R2D2_OK;
 }

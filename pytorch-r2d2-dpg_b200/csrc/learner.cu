@@ -120,6 +120,23 @@ int learner_critic_phase(Learner* l, cudaStream_t st) {
   return R2D2_OK;
 }
 
+// The actor's forward chain of the DPG update (learner.py:117,120-123 without the critic call): it reads the actor's
+// weights and the observations only - NOT the critic - so a data-parallel caller runs it while the all-reduce of the
+// critic gradients is in flight (r2d2_learner_actor_forward), before the critic's optimiser step.
+int learner_actor_forward(Learner* l, cudaStream_t st) {
+  const r2d2_learner_config& c = l->cfg;
+  const int B = c.batch, Bn = c.burn_in, L = c.learning, A = c.n_actions, O = c.obs_size;
+  const long long launches0 = launch_count();
+  const NetParams Pa = NetParams::from_flat(c.actor_params, l->actor_sh);
+  const float* obs_l = l->obs + (size_t)Bn * B * O;  // rows [Bn, Bn+L)
+  // actor from the zero state, LSTM stepped twice per row (learner.py:117,122-123); mu = output of the 2nd call
+  R2D2_TRY(net_forward(l->actor_sh, Pa, l->ws_a1, obs_l, nullptr, nullptr, nullptr, L, B, 2, st));
+  R2D2_TRY(net_head_forward(l->actor_sh, Pa, l->ws_a1, 0, L, B, 2, l->mu, A, st));
+  l->actor_forward_done = true;
+  l->launches_actor_forward = (int)(launch_count() - launches0);
+  return R2D2_OK;
+}
+
 int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t st) {
   const r2d2_learner_config& c = l->cfg;
   const int B = c.batch, Bn = c.burn_in, L = c.learning, A = c.n_actions, O = c.obs_size;
@@ -129,14 +146,17 @@ int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t st) {
   const NetParams Pc = NetParams::from_flat(c.critic_params, l->critic_sh);
   const long long LBA = (long long)L * B * A;
 
+  int extra = 0;
+  if (!l->actor_forward_done) R2D2_TRY(learner_actor_forward(l, st));   // single-GPU order: same kernels, same results
+  else extra = l->launches_actor_forward;
+  l->actor_forward_done = false;
+  const long long launches1 = launch_count();
+  (void)launches1;
   R2D2_TRY(adam_step(c.critic_params, c.critic_grads, c.critic_exp_avg, c.critic_exp_avg_sq,
                      (long long)l->critic_sh.param_count(), l->step + 1, c.critic_lr, 0.9f, 0.999f, 1e-8f,
                      grad_scale, st));                                                     // learner.py:114
 
   const float* obs_l = l->obs + (size_t)Bn * B * O;  // rows [Bn, Bn+L)
-  // actor from the zero state, LSTM stepped twice per row (learner.py:117,122-123); mu = output of the 2nd call
-  R2D2_TRY(net_forward(l->actor_sh, Pa, l->ws_a1, obs_l, nullptr, nullptr, nullptr, L, B, 2, st));
-  R2D2_TRY(net_head_forward(l->actor_sh, Pa, l->ws_a1, 0, L, B, 2, l->mu, A, st));
   // critic (post-Adam weights, zero state) on the actor's actions; loss = mean(-Q) (learner.py:118,123-124)
   R2D2_TRY(net_forward(l->critic_sh, Pc, l->ws_c2, obs_l, l->mu, nullptr, nullptr, L, B, 1, st));
   R2D2_TRY(net_head_forward(l->critic_sh, Pc, l->ws_c2, 0, L, B, 1, l->q_pi, A, st));
@@ -147,7 +167,7 @@ int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t st) {
                         l->mu, st));
   R2D2_CUDA_TRY(cudaMemsetAsync(c.actor_grads, 0, sizeof(float) * l->actor_sh.param_count(), st));
   R2D2_TRY(net_backward(l->actor_sh, Pa, &Ga, l->ws_a1, obs_l, nullptr, l->dpre_actor, 0, L, B, 2, nullptr, nullptr, st));
-  l->launches_phase[1] = (int)(launch_count() - launches0);
+  l->launches_phase[1] = (int)(launch_count() - launches0) + extra;
   return R2D2_OK;
 }
 

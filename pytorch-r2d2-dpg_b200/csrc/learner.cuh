@@ -10,6 +10,8 @@ struct Learner {
   int rows = 0;            // T' = burn_in + learning + n_step
   int step = 0;            // completed learner iterations (learner.py:82)
   int launches_phase[3] = {0, 0, 0};
+  bool actor_forward_done = false;   // learner_actor_forward already ran for the current iteration
+  int launches_actor_forward = 0;
   float* arena = nullptr;
   size_t arena_floats = 0;
   // batch (filled by replay_sample or by the caller)
@@ -25,6 +27,7 @@ struct Learner {
 int learner_create(Learner** out, const r2d2_learner_config* cfg);
 int learner_destroy(Learner* l);
 int learner_critic_phase(Learner* l, cudaStream_t stream);
+int learner_actor_forward(Learner* l, cudaStream_t stream);
 int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t stream);
 int learner_finish_phase(Learner* l, float grad_scale, cudaStream_t stream);
 

@@ -96,33 +96,51 @@ __global__ void __launch_bounds__(256) tree_recompute_range_kernel(TreeView tv, 
   tv.lvl[level][node] = node_sum(tv.lvl[level - 1] + node * TREE_K);
 }
 
-// out[t][b][w] = rows[(leaf[b] + t) * W + w]
-__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ rows, int W,
-                                                          const long long* __restrict__ leaf, int T, int B,
-                                                          float* __restrict__ out) {
-  const long long total = (long long)T * B * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(i % W);
-    const long long tb = i / W;
-    const int b = (int)(tb % B);
-    const int t = (int)(tb / B);
-    out[i] = __ldg(rows + (leaf[b] + t) * W + w);
+// One launch gathers the whole time-major batch (replay_memory.py:116-133: slice, transpose, stack, H2D in the
+// reference).  A warp owns one (t, b) pair: source row leaf[b] + t; it copies the obs row and the act row with
+// lane-contiguous accesses (16-byte vectors when the row width is a multiple of 4 floats: a row start is then 16-byte
+// aligned in both the shard and the batch), lane 0 moves the reward / terminal scalars.  Tasks >= T*B move the stored
+// recurrent states: task T*B + nh*B + b copies state_rows[leaf[b]][nh][:] to out[nh][b][:].  No division per element.
+struct GatherParams {
+  const float *obs_rows, *act_rows, *rew_rows, *term_rows, *state_rows;
+  const long long* leaf;
+  float *obs, *act, *rew, *term, *states;
+  int T, B, O, A, H;
+};
+
+__device__ __forceinline__ void warp_copy_row(const float* __restrict__ src, float* __restrict__ dst, int n, int lane) {
+  if ((n & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int k = lane; k < (n >> 2); k += 32) d4[k] = __ldg(s4 + k);
+  } else {
+    for (int k = lane; k < n; k += 32) dst[k] = __ldg(src + k);
   }
 }
 
-// out[nh][b][h] = state_rows[leaf[b]][nh][h], nh = net*2 + (hx|cx)
-__global__ void __launch_bounds__(256) gather_states_kernel(const float* __restrict__ state_rows, int H,
-                                                            const long long* __restrict__ leaf, int B,
-                                                            float* __restrict__ out) {
-  const long long total = (long long)8 * B * H;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int h = (int)(i % H);
-    const long long nb = i / H;
-    const int b = (int)(nb % B);
-    const int nh = (int)(nb / B);
-    out[i] = __ldg(state_rows + (leaf[b] * 8 + nh) * H + h);
+__global__ void __launch_bounds__(256) gather_batch_kernel(GatherParams g) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long row_tasks = (long long)g.T * g.B;
+  const long long total = row_tasks + (g.states ? (long long)8 * g.B : 0);
+  int t = (int)(warp0 / g.B), b = (int)(warp0 % g.B);                    // one division per warp, then carried
+  const int dt = (int)(n_warps / g.B), db = (int)(n_warps % g.B);
+  for (long long task = warp0; task < total; task += n_warps) {
+    if (task < row_tasks) {
+      const long long r = g.leaf[b] + t;
+      const long long o = (long long)t * g.B + b;
+      if (g.obs) warp_copy_row(g.obs_rows + r * g.O, g.obs + o * g.O, g.O, lane);
+      if (g.act) warp_copy_row(g.act_rows + r * g.A, g.act + o * g.A, g.A, lane);
+      if (lane == 0) {
+        if (g.rew) g.rew[o] = __ldg(g.rew_rows + r);
+        if (g.term) g.term[o] = __ldg(g.term_rows + r);
+      }
+    } else {
+      warp_copy_row(g.state_rows + (g.leaf[b] * 8 + (t - g.T)) * g.H, g.states + ((long long)(t - g.T) * g.B + b) * g.H, g.H, lane);
+    }
+    t += dt; b += db;
+    if (b >= g.B) { b -= g.B; ++t; }
   }
 }
 
@@ -286,11 +304,16 @@ int replay_sample(Replay* r, const float* u, int batch, long long* leaf_idx, flo
   tree_sample_kernel<<<ceil_div(batch, 256), 256, 0, stream>>>(r->tv, u, batch, leaf_idx);
   count_launch();
   const int T = r->rows_per_window, O = r->cfg.obs_size, A = r->cfg.n_actions, H = r->cfg.hidden;
-  if (obs) { gather_rows_kernel<<<grid_for((long long)T * batch * O), 256, 0, stream>>>(r->obs_rows, O, leaf_idx, T, batch, obs); count_launch(); }
-  if (act) { gather_rows_kernel<<<grid_for((long long)T * batch * A), 256, 0, stream>>>(r->act_rows, A, leaf_idx, T, batch, act); count_launch(); }
-  if (rew) { gather_rows_kernel<<<grid_for((long long)T * batch), 256, 0, stream>>>(r->rew_rows, 1, leaf_idx, T, batch, rew); count_launch(); }
-  if (term) { gather_rows_kernel<<<grid_for((long long)T * batch), 256, 0, stream>>>(r->term_rows, 1, leaf_idx, T, batch, term); count_launch(); }
-  if (states) { gather_states_kernel<<<grid_for((long long)8 * batch * H), 256, 0, stream>>>(r->state_rows, H, leaf_idx, batch, states); count_launch(); }
+  if (obs || act || rew || term || states) {
+    GatherParams g;
+    g.obs_rows = r->obs_rows; g.act_rows = r->act_rows; g.rew_rows = r->rew_rows; g.term_rows = r->term_rows;
+    g.state_rows = r->state_rows; g.leaf = leaf_idx;
+    g.obs = obs; g.act = act; g.rew = rew; g.term = term; g.states = states;
+    g.T = T; g.B = batch; g.O = O; g.A = A; g.H = H;
+    const long long tasks = (long long)T * batch + (states ? (long long)8 * batch : 0);
+    gather_batch_kernel<<<grid_for(tasks * 32), 256, 0, stream>>>(g);
+    count_launch();
+  }
   R2D2_CUDA_TRY(cudaGetLastError());
   return R2D2_OK;
 }

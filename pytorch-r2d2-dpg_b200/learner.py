@@ -8,8 +8,10 @@ so the reference's r2d2.py launcher runs unchanged - while every iteration of th
     burn-in / unrolls / BPTT -> LearnerEngine.step         (persistent cluster LSTM scans + tensor-core GEMMs)
     target, loss, priorities -> fused TD/priority kernel, written back into the sum tree on device
 
-With torch.distributed initialised (one process per GPU) each rank owns its replay shard and the two
-flat gradient buffers are all-reduced over NCCL at the optimiser steps; nothing else crosses GPUs.
+Data-parallel form: launch `learner_process` once per GPU under torchrun (RANK / LOCAL_RANK /
+WORLD_SIZE in the environment).  `Learner.__init__` then binds cuda:LOCAL_RANK, joins the NCCL process group,
+ingests only the actors i with i mod WORLD_SIZE == RANK into its own HBM replay shard, and the two flat
+gradient blocks are all-reduced at the optimiser steps; rank 0 alone writes model.pt.  Nothing else crosses GPUs.
 """
 import os
 from time import sleep, time
@@ -43,8 +45,17 @@ def learner_process(n_actors):
 class Learner:
     def __init__(self, n_actors, hidden=None, batch_size=None, device=None):
         from r2d2_b200.engine import LearnerEngine, PathConfig
+        from r2d2_b200.dist_env import DistEnv
+        self.dist_env = DistEnv.from_environ()
+        if self.dist_env.distributed:                      # one learner process per GPU
+            device = torch.device("cuda:{}".format(self.dist_env.local_rank))
+            torch.cuda.set_device(device)
+            self.dist_env.init_process_group("nccl", device=device)
         self.obs_size, self.n_actions = _env_sizes()
         self.n_actors = n_actors
+        if not self.dist_env.owned_actors(n_actors):
+            raise ValueError("rank {} of {} owns no actor: launch at most n_actors = {} learner ranks".format(
+                self.dist_env.rank, self.dist_env.world, n_actors))
         self.burn_in_length = 20
         self.learning_length = 40
         self.sequence_length = self.burn_in_length + self.learning_length
@@ -74,7 +85,10 @@ class Learner:
         return {k: v.detach().clone() for k, v in self.engine.views(net).items()}
 
     def save_model(self):
-        """model.pt = {'actor','target_actor','critic','target_critic'} state_dicts (learner.py:56-61)."""
+        """model.pt = {'actor','target_actor','critic','target_critic'} state_dicts (learner.py:56-61).
+        Replicas are identical: rank 0 alone writes."""
+        if not self.dist_env.is_main:
+            return
         model_dict = {net: self._sd(net) for net in ('actor', 'target_actor', 'critic', 'target_critic')}
         tmp = self.model_path + 'model.pt.tmp{}'.format(os.getpid())
         torch.save(model_dict, tmp)
@@ -85,7 +99,7 @@ class Learner:
         self.engine.flat['target_critic'].copy_(self.engine.flat['critic'])
 
     def _ingest(self):
-        for i in range(self.n_actors):
+        for i in self.dist_env.owned_actors(self.n_actors):   # all of them in a single-process run (learner.py:70-73)
             if os.path.isfile(self.memory_path + '/memory{}.pt'.format(i)):
                 self.memory.load(i)
 
@@ -93,11 +107,12 @@ class Learner:
         while self.memory.sequence_counter < self.batch_size * 100:   # warm-up gate, learner.py:69-75
             self._ingest()
             sleep(0.1)
-            print('learner memory sequence size:', self.memory.sequence_counter)
+            if self.dist_env.is_main:
+                print('learner memory sequence size:', self.memory.sequence_counter)
         step = 0
         dev = self.memory._dev
         while max_steps is None or step < max_steps:
-            if step % 100 == 0:
+            if step % 100 == 0 and self.dist_env.is_main:
                 print('learning step:', step)
             step += 1
             dev.sample_into(self.engine)                               # learner.py:84

@@ -128,6 +128,7 @@ class LearnerEngine:
         self.losses = nv.view_f32(b.losses, (2,), dev)
         self.world = 1
         self._dist = None
+        self._sync = None
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -158,14 +159,36 @@ class LearnerEngine:
         put("target_actor", target_actor if target_actor is not None else actor)
         put("target_critic", target_critic if target_critic is not None else critic)
 
-    def enable_data_parallel(self):
-        """Gradients are averaged over ranks at the two optimiser steps (NCCL all-reduce of the flat buffers)."""
+    def enable_data_parallel(self, require: bool | None = None):
+        """Gradients are averaged over ranks at the two optimiser steps (NCCL all-reduce of the flat buffers on a
+        side stream; the critic's overlaps with the actor's forward chain).  `require` (default: WORLD_SIZE > 1 in the
+        environment) turns a missing process group into an error instead of N silently independent learners."""
+        import os
         import torch.distributed as dist
+        from .dist_env import GradSync
+        if require is None:
+            require = int(os.environ.get("WORLD_SIZE", "1")) > 1
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self._dist = dist
             self.world = dist.get_world_size()
+            self._sync = GradSync(dist, self.world)
             for net in ("actor", "critic", "target_actor", "target_critic"):
                 dist.broadcast(self.flat[net], src=0)
+            for d in (self.exp_avg, self.exp_avg_sq):
+                for net in ("actor", "critic"):
+                    dist.broadcast(d[net], src=0)
+        elif require:
+            raise nv.NativeError("WORLD_SIZE > 1 but torch.distributed is not initialised: call "
+                                 "r2d2_b200.dist_env.DistEnv.from_environ().init_process_group() first "
+                                 "(the drop-in learner.Learner does)")
+
+    def replicas_identical(self) -> bool:
+        """Data-parallel invariant: parameters and Adam moments are bit-identical on every rank."""
+        if self._dist is None:
+            return True
+        ts = [self.flat[n] for n in ("actor", "critic", "target_actor", "target_critic")]
+        ts += [d[n] for d in (self.exp_avg, self.exp_avg_sq) for n in ("actor", "critic")]
+        return self._sync.replicas_identical(ts)
 
     # ---- batch ------------------------------------------------------------------------------
     def set_batch(self, batch: dict):
@@ -185,10 +208,13 @@ class LearnerEngine:
         scale = 1.0 / self.world
         nv.check(self.lib.r2d2_learner_critic_phase(self._h, s))
         if self._dist is not None:
-            self._dist.all_reduce(self.grads["critic"])
+            self._sync.start(self.grads["critic"])                       # side stream
+            nv.check(self.lib.r2d2_learner_actor_forward(self._h, s))    # reads no critic weights: overlaps the all-reduce
+            self._sync.wait(self.device)
         nv.check(self.lib.r2d2_learner_actor_phase(self._h, scale, s))
         if self._dist is not None:
-            self._dist.all_reduce(self.grads["actor"])
+            self._sync.start(self.grads["actor"])
+            self._sync.wait(self.device)
         nv.check(self.lib.r2d2_learner_finish_phase(self._h, scale, s))
 
     @property

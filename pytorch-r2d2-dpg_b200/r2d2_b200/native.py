@@ -101,6 +101,7 @@ SIGNATURES = {
     "r2d2_learner_destroy": (c_int, [c_void_p]),
     "r2d2_learner_buffers_get": (c_int, [c_void_p, POINTER(LearnerBuffers)]),
     "r2d2_learner_critic_phase": (c_int, [c_void_p, c_void_p]),
+    "r2d2_learner_actor_forward": (c_int, [c_void_p, c_void_p]),
     "r2d2_learner_actor_phase": (c_int, [c_void_p, c_float, c_void_p]),
     "r2d2_learner_finish_phase": (c_int, [c_void_p, c_float, c_void_p]),
     "r2d2_learner_step_count": (c_int, [c_void_p]),

@@ -61,3 +61,44 @@ def test_two_gpu_data_parallel_matches_single_gpu():
             upd, ref = r0[k] - one["init/" + k], one[k] - one["init/" + k]
             assert rel_l2(r0[k], one[k]) < 1e-4, k                      # parameters
             assert rel_l2(upd, ref) < 5e-2, k                           # and the (Adam, sign-like) updates agree
+
+
+def test_torchrun_dropin_learner():
+    """The PRODUCT path, not a harness: `learner.Learner` launched once per GPU by torch.distributed.run binds
+    cuda:LOCAL_RANK, joins NCCL, ingests only the actor files i = rank mod world (the reference's single learner polls all
+    of them, learner.py:69-75,144-149), keeps its replicas bit-identical and lets rank 0 alone write model.pt."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "pytorch-r2d2-dpg_b200")]
+    env = dict(os.environ, R2D2_OBS_SIZE="5", R2D2_N_ACTIONS="2", R2D2_HIDDEN="64", R2D2_BATCH="4",
+               R2D2_ACTOR_DEVICE="cpu")
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "model_data"))
+        os.makedirs(os.path.join(d, "memory_data"))
+        # four CPU actors write episode files in the reference's format (actor.py:163-179)
+        code = ("import sys; sys.path[:0]=[%r,%r]; import actor\n"
+                "for aid in range(4):\n"
+                "    a = actor.Actor(aid); a.env.episode_len = 150; a.run(max_episodes=5)\n") % (
+                    root, os.path.join(root, "pytorch-r2d2-dpg_b200"))
+        # actors need a model.pt to follow: a single-process learner writes the initial one
+        init = ("import sys; sys.path[:0]=[%r,%r]; import learner; learner.Learner(4)\n") % (
+            root, os.path.join(root, "pytorch-r2d2-dpg_b200"))
+        subprocess.check_call([sys.executable, "-c", init], cwd=d, env=env)
+        subprocess.check_call([sys.executable, "-c", code], cwd=d, env=env)
+        os.remove(os.path.join(d, "model_data", "model.pt"))
+        port = 29800 + os.getpid() % 100
+        subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                               "--master-addr", "127.0.0.1", "--master-port", str(port),
+                               os.path.join(root, "tests", "dp_dropin_worker.py"), "4", "4"], cwd=d, env=env, timeout=600)
+        r = [json.load(open(os.path.join(d, "dp_rank%d.json" % i))) for i in range(2)]
+        assert [x["device"] for x in r] == ["cuda:0", "cuda:1"]
+        assert r[0]["owned"] == [0, 2] and r[1]["owned"] == [1, 3]
+        assert r[0]["episodes"] > 0 and r[1]["episodes"] > 0
+        assert r[0]["steps"] == r[1]["steps"] == 4
+        assert r[0]["replicas_identical"] and r[1]["replicas_identical"]
+        assert r[0]["param_sum"] == r[1]["param_sum"]
+        assert os.path.isfile(os.path.join(d, "model_data", "model.pt"))        # written by rank 0 alone
