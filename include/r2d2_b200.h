@@ -116,6 +116,18 @@ int r2d2_td_priority(const float* q, const float* q_next, const float* rew, cons
                      int A, int burn_in, int n_step, float gamma, float eta, float* target, float* dq,
                      float* td_sq, float* priority, float* critic_loss, r2d2_stream_t stream);
 
+/* Actor-side rows of the path, batched over finished episodes (one episode per batch column, time-major,
+ * zero padded): n-step discounted reward pre-sum (actor.py:74-76; rows i < n_rows[b] - n_step, later rows copied) and
+ * the initial sequence priorities (actor.py:78-107): priority k = eta*max + (1-eta)*mean over j = k+burn_in+1 ..
+ * k+burn_in+learning of (mean_A(q[j] - h(R[j] + gamma^n (1-term[j+n-1]) q_next[j+n])))^2 - the reference's deque is one
+ * step ahead of the learner's window and squares the MEAN difference; both are kept.  prio [B, p_max], zero where
+ * k >= n_rows[b] - n_step - burn_in - learning.  q, q_next come from r2d2_lstm_net_forward on the zero state. */
+int r2d2_nstep_rewards(const float* raw, const int* n_rows, int T, int B, int n_step, float gamma, float* out,
+                       r2d2_stream_t stream);
+int r2d2_actor_priorities(const float* q, const float* q_next, const float* rew, const float* term, const int* n_rows,
+                          int B, int A, int burn_in, int learning, int n_step, float gamma, float eta, int p_max,
+                          float* prio, r2d2_stream_t stream);
+
 /* torch.optim.Adam defaults (learner.py:50-53,114,128) on a flat buffer; grad is multiplied by grad_scale first. */
 int r2d2_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step,
                    float lr, float beta1, float beta2, float eps, float grad_scale, r2d2_stream_t stream);
@@ -146,11 +158,26 @@ int r2d2_replay_add_episode(r2d2_replay_t* r, const float* obs, const float* act
                             const float* term, const float* states, int n_rows, int n_state_rows,
                             const float* priority, int n_starts, r2d2_stream_t stream);
 
+/* One actor file at a time (LearnerReplayMemory.load, replay_memory.py:138-157): all episodes of the file are appended,
+ * THEN the oldest episodes are dropped while the sequence counter exceeds max_sequences - the reference's order.
+ * HOST pointers, packed over the file's episodes with R = sum(n_rows): obs [R,O], act [R,A], rew [R], term [R],
+ * states [R,4,2,H] (zero rows for the pad rows), leaf_prio [R] (the priority of a row that starts a sequence, else 0).
+ * Contiguous runs in the ring are one copy per tensor; the tree is refreshed once; one stream synchronisation.
+ * Outputs (host, optional): first ring row of each episode, episodes evicted by this call, the sequence counter. */
+int r2d2_replay_add_episodes(r2d2_replay_t* r, int n_episodes, const int* n_rows, const int* n_starts,
+                             const float* obs, const float* act, const float* rew, const float* term,
+                             const float* states, const float* leaf_prio, long long* row_start_out,
+                             long long* n_evicted_out, long long* sequence_counter_out, r2d2_stream_t stream);
+
 /* Draw `batch` starts from DEVICE uniforms u[batch] in [0,1) and gather the time-major batch:
  * leaf_idx [batch] (int64, start row = tree leaf), obs [T',batch,O], act [T',batch,A], rew [T',batch],
  * term [T',batch], states [4,2,batch,H].  Any gather output may be NULL. */
 int r2d2_replay_sample(r2d2_replay_t* r, const float* u, int batch, long long* leaf_idx, float* obs, float* act,
                        float* rew, float* term, float* states, r2d2_stream_t stream);
+
+/* The gather half alone, for start rows the caller chose (DEVICE int64 leaf_idx): same outputs as r2d2_replay_sample. */
+int r2d2_replay_gather(r2d2_replay_t* r, const long long* leaf_idx, int batch, float* obs, float* act, float* rew,
+                       float* term, float* states, r2d2_stream_t stream);
 
 /* priority[leaf_idx[i]] = prio[i] (DEVICE arrays; on duplicates the highest i wins, like the python
  * loop at learner.py:136-139) and recompute the touched tree paths. */

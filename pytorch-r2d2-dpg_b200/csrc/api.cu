@@ -142,6 +142,16 @@ int r2d2_td_priority(const float* q, const float* q_next, const float* rew, cons
   return td_priority(p, S(stream));
 }
 
+int r2d2_nstep_rewards(const float* raw, const int* n_rows, int T, int B, int n_step, float gamma, float* out,
+                       r2d2_stream_t stream) {
+  return nstep_rewards(raw, n_rows, T, B, n_step, gamma, out, S(stream));
+}
+int r2d2_actor_priorities(const float* q, const float* q_next, const float* rew, const float* term, const int* n_rows,
+                          int B, int A, int burn_in, int learning, int n_step, float gamma, float eta, int p_max,
+                          float* prio, r2d2_stream_t stream) {
+  return actor_priorities(q, q_next, rew, term, n_rows, B, A, burn_in, learning, n_step, gamma, eta, p_max, prio, S(stream));
+}
+
 int r2d2_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step,
                    float lr, float beta1, float beta2, float eps, float grad_scale, r2d2_stream_t stream) {
   return adam_step(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, grad_scale, S(stream));
@@ -158,9 +168,20 @@ int r2d2_replay_add_episode(r2d2_replay_t* r, const float* obs, const float* act
   return replay_add_episode(reinterpret_cast<Replay*>(r), obs, act, rew, term, states, n_rows, n_state_rows, priority,
                             n_starts, S(stream));
 }
+int r2d2_replay_add_episodes(r2d2_replay_t* r, int n_episodes, const int* n_rows, const int* n_starts,
+                             const float* obs, const float* act, const float* rew, const float* term,
+                             const float* states, const float* leaf_prio, long long* row_start_out,
+                             long long* n_evicted_out, long long* sequence_counter_out, r2d2_stream_t stream) {
+  return replay_add_episodes(reinterpret_cast<Replay*>(r), n_episodes, n_rows, n_starts, obs, act, rew, term, states,
+                             leaf_prio, row_start_out, n_evicted_out, sequence_counter_out, S(stream));
+}
 int r2d2_replay_sample(r2d2_replay_t* r, const float* u, int batch, long long* leaf_idx, float* obs, float* act,
                        float* rew, float* term, float* states, r2d2_stream_t stream) {
   return replay_sample(reinterpret_cast<Replay*>(r), u, batch, leaf_idx, obs, act, rew, term, states, S(stream));
+}
+int r2d2_replay_gather(r2d2_replay_t* r, const long long* leaf_idx, int batch, float* obs, float* act, float* rew,
+                       float* term, float* states, r2d2_stream_t stream) {
+  return replay_gather(reinterpret_cast<Replay*>(r), leaf_idx, batch, obs, act, rew, term, states, S(stream));
 }
 int r2d2_replay_update_priorities(r2d2_replay_t* r, const long long* leaf_idx, const float* prio, int batch,
                                   r2d2_stream_t stream) {

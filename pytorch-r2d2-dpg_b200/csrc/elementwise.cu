@@ -3,6 +3,8 @@
 // bias-gradient column sums, small reductions.
 #include "elementwise.cuh"
 
+#include <cmath>
+
 namespace r2d2 {
 namespace {
 
@@ -211,7 +213,76 @@ __global__ void mul_dtanh_kernel(const float* __restrict__ d_out, const float* _
     d_pre[i] = d_out[i] * (1.0f - out[i] * out[i]);
 }
 
+// ---- actor-side next rows: n-step reward pre-sum (actor.py:74-76) and the initial priorities of a
+// finished episode (actor.py:78-107), batched over episodes (time-major [T,B], one episode per batch column, zero
+// padded past its last row).
+__global__ void __launch_bounds__(256) nstep_reward_kernel(const float* __restrict__ raw, const int* __restrict__ n_rows,
+                                                           int T, int B, int n_step, float gamma, float* __restrict__ out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * B) return;
+  const int i = (int)(idx / B), b = (int)(idx % B);
+  float v = raw[idx];
+  if (i < n_rows[b] - n_step) {   // rows of the real episode: discounted sum of the next n raw rewards
+    double acc = 0.0, g = 1.0;
+    for (int j = 0; j < n_step; ++j) { acc += (double)raw[(size_t)(i + j) * B + b] * g; g *= (double)gamma; }
+    v = (float)acc;
+  }
+  out[idx] = v;
+}
+
+// priority k of episode b: 0.9 max + 0.1 mean over j = k+Bn+1 .. k+Bn+L of td_j^2,
+// td_j = mean_A(q[j,b,:] - h(R[j,b] + gamma^n (1 - term[j+n-1,b]) q_next[j+n,b,:]))  -  the reference's deque of
+// `learning` entries is one step ahead of the window the learner trains on (actor.py:102-107), reproduced here.
+__global__ void __launch_bounds__(128) actor_priority_kernel(const float* __restrict__ q, const float* __restrict__ q_next,
+                                                             const float* __restrict__ rew, const float* __restrict__ term,
+                                                             const int* __restrict__ n_rows, int B, int A, int burn_in,
+                                                             int learning, int n_step, float gamma_n, float eta,
+                                                             int p_max, float* __restrict__ prio) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p_max) return;
+  const int E = n_rows[b] - n_step;
+  float out = 0.f;
+  if (k < E - (burn_in + learning)) {
+    float mx = -INFINITY, sum = 0.f;
+    for (int j = k + burn_in + 1; j <= k + burn_in + learning; ++j) {
+      const float r = rew[(size_t)j * B + b];
+      const float cont = gamma_n * (1.0f - term[(size_t)(j + n_step - 1) * B + b]);
+      const float* qj = q + ((size_t)j * B + b) * A;
+      const float* qn = q_next + ((size_t)(j + n_step) * B + b) * A;
+      float acc = 0.f;
+      for (int a = 0; a < A; ++a) acc += qj[a] - value_rescale(r + cont * qn[a]);
+      const float td = acc / (float)A;
+      const float sq = td * td;
+      mx = fmaxf(mx, sq);
+      sum += sq;
+    }
+    out = eta * mx + (1.0f - eta) * (sum / (float)learning);
+  }
+  prio[(size_t)b * p_max + k] = out;
+}
+
 }  // namespace
+
+int nstep_rewards(const float* raw, const int* n_rows, int T, int B, int n_step, float gamma, float* out, cudaStream_t stream) {
+  R2D2_REQUIRE(raw && n_rows && out && raw != out && T > 0 && B > 0 && n_step > 0, "nstep_rewards args");
+  nstep_reward_kernel<<<(unsigned)(((long long)T * B + 255) / 256), 256, 0, stream>>>(raw, n_rows, T, B, n_step, gamma, out);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+int actor_priorities(const float* q, const float* q_next, const float* rew, const float* term, const int* n_rows, int B,
+                     int A, int burn_in, int learning, int n_step, float gamma, float eta, int p_max, float* prio,
+                     cudaStream_t stream) {
+  R2D2_REQUIRE(q && q_next && rew && term && n_rows && prio && B > 0 && A > 0 && p_max > 0, "actor_priorities args");
+  const float gamma_n = (float)std::pow((double)gamma, (double)n_step);
+  actor_priority_kernel<<<dim3(ceil_div(p_max, 128), B), 128, 0, stream>>>(q, q_next, rew, term, n_rows, B, A, burn_in, learning,
+                                                                           n_step, gamma_n, eta, p_max, prio);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
 
 int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t stream) {
   add_vec_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(a, b, out, n);

@@ -19,6 +19,12 @@ struct TdPriorityParams {
 };
 
 int td_priority(const TdPriorityParams& p, cudaStream_t stream);
+// actor-side next rows (actor.py:74-107), batched over episodes: raw / out [T,B] time-major, n_rows[b] = rows of episode b
+// incl. its n_step pad rows; q [T-n_step.., B, A] online critic, q_next [T,B,A] target critic on target-actor actions
+int nstep_rewards(const float* raw, const int* n_rows, int T, int B, int n_step, float gamma, float* out, cudaStream_t stream);
+int actor_priorities(const float* q, const float* q_next, const float* rew, const float* term, const int* n_rows, int B,
+                     int A, int burn_in, int learning, int n_step, float gamma, float eta, int p_max, float* prio,
+                     cudaStream_t stream);
 // out[n] += sum_m x[m,n] (and out2 if given); accumulates into pre-zeroed buffers
 int colsum(const float* x, long long ld, int M, int N, float* out, float* out2, cudaStream_t stream);
 int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t stream);

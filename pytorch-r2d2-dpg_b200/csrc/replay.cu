@@ -7,6 +7,7 @@
 // every node is the left-to-right fp32 sum of its 32 children (one 128-byte line), so the tree has
 // ceil(log32(cap)) levels (5 for 2M rows) instead of 21 dependent loads of a binary tree, and the
 // CUDA tree and its C restatement (oracle/sumtree_oracle.c) are bit-identical by construction.
+#include <algorithm>
 #include <deque>
 #include <map>
 #include <vector>
@@ -172,6 +173,7 @@ struct Replay {
   long long head = 0;
   long long sequence_counter = 0;
   long long rows_used = 0;
+  long long evicted_total = 0;
 };
 
 static int recompute_ancestors(Replay* r, long long first_leaf, long long n_leaves, cudaStream_t stream) {
@@ -236,18 +238,68 @@ int replay_destroy(Replay* r) {
   return R2D2_OK;
 }
 
-static int evict_front(Replay* r, cudaStream_t stream) {
+// Ranges of leaves whose ancestors must be refreshed; merged and recomputed once per ingest call.
+typedef std::vector<std::pair<long long, long long>> RangeList;   // (first leaf, count)
+
+static int refresh_ranges(Replay* r, RangeList& ranges, cudaStream_t stream) {
+  if (ranges.empty()) return R2D2_OK;
+  std::sort(ranges.begin(), ranges.end());
+  long long lo = ranges[0].first, hi = ranges[0].first + ranges[0].second;
+  for (size_t i = 1; i <= ranges.size(); ++i) {
+    // merge ranges that share a parent node (distance < fan-out): one launch chain instead of two
+    if (i < ranges.size() && ranges[i].first <= hi + TREE_K) {
+      hi = std::max(hi, ranges[i].first + ranges[i].second);
+      continue;
+    }
+    R2D2_TRY(recompute_ancestors(r, lo, hi - lo, stream));
+    if (i < ranges.size()) { lo = ranges[i].first; hi = ranges[i].first + ranges[i].second; }
+  }
+  ranges.clear();
+  return R2D2_OK;
+}
+
+static int evict_front(Replay* r, cudaStream_t stream, RangeList* deferred) {
   const Episode e = r->episodes.front();
   r->episodes.pop_front();
   r->by_row.erase(e.row_start);
   // replay_memory.py:149: the counter drops by len(episode) - sequence_length (sic: not the amount added at :147)
   r->sequence_counter -= e.n_rows - (r->cfg.burn_in + r->cfg.learning);
   r->rows_used -= e.n_rows;
+  ++r->evicted_total;
   if (e.n_starts > 0) {
     R2D2_CUDA_TRY(cudaMemsetAsync(r->tv.lvl[0] + e.row_start, 0, sizeof(float) * e.n_starts, stream));
-    R2D2_TRY(recompute_ancestors(r, e.row_start, e.n_starts, stream));
+    if (deferred) deferred->push_back({e.row_start, (long long)e.n_starts});
+    else R2D2_TRY(recompute_ancestors(r, e.row_start, e.n_starts, stream));
   }
   return R2D2_OK;
+}
+
+// Ring placement of an episode of n_rows rows: wrap when the tail gap is too small, then evict - oldest first, the
+// reference's FIFO order (replay_memory.py:148-152) - until no live episode overlaps [start, start + n_rows).  After a
+// wrap the oldest episode may sit at the TAIL of the ring while a younger one occupies the head that is about to be
+// overwritten: evicting from the front until the overlap is gone removes both (the earlier loop stopped at
+// the first non-overlapping front episode and then failed the overlap check).
+static int place_episode(Replay* r, int n_rows, cudaStream_t stream, RangeList* deferred, long long* start_out) {
+  R2D2_REQUIRE(n_rows <= r->cfg.capacity_rows, "episode larger than the ring");
+  if (r->head + n_rows > r->cfg.capacity_rows) r->head = 0;  // wrap: the tail gap stays unused
+  const long long start = r->head, end = start + n_rows;
+  auto overlaps = [&]() {
+    for (const Episode& e : r->episodes)
+      if (e.row_start < end && start < e.row_start + e.n_rows) return true;
+    return false;
+  };
+  while (!r->episodes.empty() && overlaps()) R2D2_TRY(evict_front(r, stream, deferred));
+  *start_out = start;
+  return R2D2_OK;
+}
+
+static void commit_episode(Replay* r, long long start, int n_rows, int n_starts) {
+  Episode e{start, n_rows, n_starts, r->next_serial++};
+  r->episodes.push_back(e);
+  r->by_row[start] = e.serial;
+  r->head = start + n_rows;
+  r->rows_used += n_rows;
+  r->sequence_counter += n_rows - (r->rows_per_window - 1);  // replay_memory.py:147
 }
 
 int replay_add_episode(Replay* r, const float* obs, const float* act, const float* rew, const float* term,
@@ -258,18 +310,10 @@ int replay_add_episode(Replay* r, const float* obs, const float* act, const floa
   R2D2_REQUIRE(n_starts >= 0 && n_starts <= n_rows - r->rows_per_window + 1, "n_starts exceeds valid window starts");
   R2D2_REQUIRE(n_state_rows >= n_starts && n_state_rows <= n_rows, "state rows");
   R2D2_REQUIRE(n_starts == 0 || priority, "priority");
-  R2D2_REQUIRE(n_rows <= r->cfg.capacity_rows, "episode larger than the ring");
   const int O = r->cfg.obs_size, A = r->cfg.n_actions, H = r->cfg.hidden;
-  if (r->head + n_rows > r->cfg.capacity_rows) r->head = 0;  // wrap: the tail gap stays unused
-  const long long start = r->head, end = start + n_rows;
-  while (!r->episodes.empty()) {
-    const Episode& f = r->episodes.front();
-    const bool overlap = f.row_start < end && start < f.row_start + f.n_rows;
-    if (!overlap) break;
-    R2D2_TRY(evict_front(r, stream));
-  }
-  for (const Episode& e : r->episodes)
-    R2D2_REQUIRE(!(e.row_start < end && start < e.row_start + e.n_rows), "ring overlap with a live episode");
+  RangeList ranges;
+  long long start = 0;
+  R2D2_TRY(place_episode(r, n_rows, stream, &ranges, &start));
   R2D2_CUDA_TRY(cudaMemcpyAsync(r->obs_rows + start * O, obs, sizeof(float) * (size_t)n_rows * O, cudaMemcpyHostToDevice, stream));
   R2D2_CUDA_TRY(cudaMemcpyAsync(r->act_rows + start * A, act, sizeof(float) * (size_t)n_rows * A, cudaMemcpyHostToDevice, stream));
   R2D2_CUDA_TRY(cudaMemcpyAsync(r->rew_rows + start, rew, sizeof(float) * (size_t)n_rows, cudaMemcpyHostToDevice, stream));
@@ -284,25 +328,73 @@ int replay_add_episode(Replay* r, const float* obs, const float* act, const floa
                                   cudaMemcpyHostToDevice, stream));
   if (n_rows > n_starts)
     R2D2_CUDA_TRY(cudaMemsetAsync(r->tv.lvl[0] + start + n_starts, 0, sizeof(float) * (size_t)(n_rows - n_starts), stream));
-  R2D2_TRY(recompute_ancestors(r, start, n_rows, stream));
-  Episode e{start, n_rows, n_starts, r->next_serial++};
-  r->episodes.push_back(e);
-  r->by_row[start] = e.serial;
-  r->head = end;
-  r->rows_used += n_rows;
-  r->sequence_counter += n_rows - (r->rows_per_window - 1);  // replay_memory.py:147
+  ranges.push_back({start, (long long)n_rows});
+  commit_episode(r, start, n_rows, n_starts);
   while (r->cfg.max_sequences > 0 && r->sequence_counter > r->cfg.max_sequences && r->episodes.size() > 1)
-    R2D2_TRY(evict_front(r, stream));
+    R2D2_TRY(evict_front(r, stream, &ranges));
+  R2D2_TRY(refresh_ranges(r, ranges, stream));
   R2D2_CUDA_TRY(cudaStreamSynchronize(stream));  // host buffers may be released by the caller
   return R2D2_OK;
 }
 
-int replay_sample(Replay* r, const float* u, int batch, long long* leaf_idx, float* obs, float* act, float* rew,
-                  float* term, float* states, cudaStream_t stream) {
-  R2D2_REQUIRE(r && u && leaf_idx && batch > 0, "args");
-  R2D2_REQUIRE(!r->episodes.empty(), "replay is empty");
-  tree_sample_kernel<<<ceil_div(batch, 256), 256, 0, stream>>>(r->tv, u, batch, leaf_idx);
-  count_launch();
+// One actor file at a time (LearnerReplayMemory.load, replay_memory.py:138-157): every episode of the file is appended,
+// THEN the oldest episodes are dropped while the sequence counter exceeds the cap - the reference's order.  The rows
+// of all episodes arrive packed ([R, *] with R = sum of n_rows; recurrent states zero-padded to R rows, leaf
+// priorities already expanded to one value per row): contiguous runs in the ring are one copy per tensor, the sum tree
+// is refreshed once over the merged touched ranges, and there is one stream synchronisation per file.
+int replay_add_episodes(Replay* r, int n_episodes, const int* n_rows, const int* n_starts, const float* obs,
+                        const float* act, const float* rew, const float* term, const float* states,
+                        const float* leaf_prio, long long* row_start_out, long long* n_evicted_out,
+                        long long* sequence_counter_out, cudaStream_t stream) {
+  R2D2_REQUIRE(r && n_episodes >= 0 && (n_episodes == 0 || (n_rows && n_starts && obs && act && rew && term && states && leaf_prio)),
+               "null");
+  const int O = r->cfg.obs_size, A = r->cfg.n_actions, H = r->cfg.hidden;
+  for (int e = 0; e < n_episodes; ++e) {
+    R2D2_REQUIRE(n_rows[e] >= r->rows_per_window, "episode shorter than one window");
+    R2D2_REQUIRE(n_starts[e] >= 0 && n_starts[e] <= n_rows[e] - r->rows_per_window + 1, "n_starts exceeds valid window starts");
+    R2D2_REQUIRE(n_rows[e] <= r->cfg.capacity_rows, "episode larger than the ring");
+  }
+  const long long evicted0 = r->evicted_total;
+  RangeList ranges;
+  long long src = 0;                    // first packed row of the current run
+  long long run_start = -1, run_rows = 0;
+  auto flush = [&]() -> int {
+    if (run_rows == 0) return R2D2_OK;
+    const size_t n = (size_t)run_rows;
+    R2D2_CUDA_TRY(cudaMemcpyAsync(r->obs_rows + run_start * O, obs + src * O, sizeof(float) * n * O, cudaMemcpyHostToDevice, stream));
+    R2D2_CUDA_TRY(cudaMemcpyAsync(r->act_rows + run_start * A, act + src * A, sizeof(float) * n * A, cudaMemcpyHostToDevice, stream));
+    R2D2_CUDA_TRY(cudaMemcpyAsync(r->rew_rows + run_start, rew + src, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+    R2D2_CUDA_TRY(cudaMemcpyAsync(r->term_rows + run_start, term + src, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+    R2D2_CUDA_TRY(cudaMemcpyAsync(r->state_rows + run_start * 8 * H, states + src * 8 * H, sizeof(float) * n * 8 * H,
+                                  cudaMemcpyHostToDevice, stream));
+    R2D2_CUDA_TRY(cudaMemcpyAsync(r->tv.lvl[0] + run_start, leaf_prio + src, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+    ranges.push_back({run_start, run_rows});
+    src += run_rows;
+    run_rows = 0;
+    return R2D2_OK;
+  };
+  for (int e = 0; e < n_episodes; ++e) {
+    long long start = 0;
+    R2D2_TRY(place_episode(r, n_rows[e], stream, &ranges, &start));
+    if (run_rows > 0 && start != run_start + run_rows) R2D2_TRY(flush());   // the ring wrapped: new run
+    if (run_rows == 0) run_start = start;
+    run_rows += n_rows[e];
+    commit_episode(r, start, n_rows[e], n_starts[e]);
+    if (row_start_out) row_start_out[e] = start;
+  }
+  R2D2_TRY(flush());
+  while (r->cfg.max_sequences > 0 && r->sequence_counter > r->cfg.max_sequences && !r->episodes.empty())
+    R2D2_TRY(evict_front(r, stream, &ranges));                               // replay_memory.py:148-152
+  R2D2_TRY(refresh_ranges(r, ranges, stream));
+  R2D2_CUDA_TRY(cudaStreamSynchronize(stream));  // host buffers may be released by the caller
+  if (n_evicted_out) *n_evicted_out = r->evicted_total - evicted0;
+  if (sequence_counter_out) *sequence_counter_out = r->sequence_counter;
+  return R2D2_OK;
+}
+
+int replay_gather(Replay* r, const long long* leaf_idx, int batch, float* obs, float* act, float* rew, float* term,
+                  float* states, cudaStream_t stream) {
+  R2D2_REQUIRE(r && leaf_idx && batch > 0, "args");
   const int T = r->rows_per_window, O = r->cfg.obs_size, A = r->cfg.n_actions, H = r->cfg.hidden;
   if (obs || act || rew || term || states) {
     GatherParams g;
@@ -316,6 +408,16 @@ int replay_sample(Replay* r, const float* u, int batch, long long* leaf_idx, flo
   }
   R2D2_CUDA_TRY(cudaGetLastError());
   return R2D2_OK;
+}
+
+int replay_sample(Replay* r, const float* u, int batch, long long* leaf_idx, float* obs, float* act, float* rew,
+                  float* term, float* states, cudaStream_t stream) {
+  R2D2_REQUIRE(r && u && leaf_idx && batch > 0, "args");
+  R2D2_REQUIRE(!r->episodes.empty(), "replay is empty");
+  tree_sample_kernel<<<ceil_div(batch, 256), 256, 0, stream>>>(r->tv, u, batch, leaf_idx);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return replay_gather(r, leaf_idx, batch, obs, act, rew, term, states, stream);
 }
 
 int replay_update_priorities(Replay* r, const long long* leaf_idx, const float* prio, int batch, cudaStream_t stream) {

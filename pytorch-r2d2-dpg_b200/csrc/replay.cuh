@@ -18,8 +18,14 @@ int replay_destroy(Replay* r);
 int replay_add_episode(Replay* r, const float* obs, const float* act, const float* rew, const float* term,
                        const float* states, int n_rows, int n_state_rows, const float* priority, int n_starts,
                        cudaStream_t stream);
+int replay_add_episodes(Replay* r, int n_episodes, const int* n_rows, const int* n_starts, const float* obs,
+                        const float* act, const float* rew, const float* term, const float* states,
+                        const float* leaf_prio, long long* row_start_out, long long* n_evicted_out,
+                        long long* sequence_counter_out, cudaStream_t stream);
 int replay_sample(Replay* r, const float* u, int batch, long long* leaf_idx, float* obs, float* act, float* rew,
                   float* term, float* states, cudaStream_t stream);
+int replay_gather(Replay* r, const long long* leaf_idx, int batch, float* obs, float* act, float* rew, float* term,
+                  float* states, cudaStream_t stream);
 int replay_update_priorities(Replay* r, const long long* leaf_idx, const float* prio, int batch, cudaStream_t stream);
 int replay_stats(Replay* r, r2d2_replay_stats_t* out, cudaStream_t stream);
 int replay_decode(Replay* r, const long long* leaf_host, int n, long long* episode_index, long long* sequence_index);

@@ -263,6 +263,40 @@ class DeviceReplay:
         nv.check(self.lib.r2d2_replay_add_episode(self._h, po, pa, pr, pt, ps, obs.shape[0], states.shape[0], pp,
                                                   priority.shape[0], nv.current_stream()))
 
+    def add_episodes(self, episodes):
+        """One actor file in one native call (LearnerReplayMemory.load, replay_memory.py:138-157).  `episodes`: list of
+        (obs [n,O], act [n,A], rew [n], term [n], states [n_real,4,2,H], priority [n_starts]) host arrays.  Returns
+        (row_start per episode, episodes evicted by the call, sequence counter)."""
+        if not episodes:
+            return [], 0, None
+        n_rows = np.asarray([e[0].shape[0] for e in episodes], np.int32)
+        n_starts = np.asarray([len(e[5]) for e in episodes], np.int32)
+        R, H = int(n_rows.sum()), self.cfg.hidden
+        obs = np.concatenate([np.asarray(e[0], np.float32) for e in episodes])
+        act = np.concatenate([np.asarray(e[1], np.float32) for e in episodes])
+        rew = np.concatenate([np.asarray(e[2], np.float32).reshape(-1) for e in episodes])
+        term = np.concatenate([np.asarray(e[3], np.float32).reshape(-1) for e in episodes])
+        states = np.zeros((R, 4, 2, H), np.float32)
+        leaf = np.zeros(R, np.float32)
+        off = 0
+        for e, n in zip(episodes, n_rows):
+            st = np.asarray(e[4], np.float32)
+            if st.shape[1:] != (4, 2, H) or st.shape[0] > n:
+                raise ValueError("recurrent states %r do not fit an episode of %d rows at hidden %d" % (st.shape, n, H))
+            states[off:off + st.shape[0]] = st
+            leaf[off:off + len(e[5])] = np.asarray(e[5], np.float32).reshape(-1)
+            off += int(n)
+        if obs.shape != (R, self.cfg.obs) or act.shape != (R, self.cfg.act):
+            raise ValueError("episode rows %r / %r do not match the shard (obs %d, act %d)" % (obs.shape, act.shape,
+                                                                                           self.cfg.obs, self.cfg.act))
+        starts = np.zeros(len(episodes), np.int64)
+        n_evicted, counter = c_longlong(0), c_longlong(0)
+        P = lambda a: a.ctypes.data_as(c_void_p)  # noqa: E731
+        nv.check(self.lib.r2d2_replay_add_episodes(self._h, len(episodes), P(n_rows), P(n_starts), P(obs), P(act), P(rew),
+                                                   P(term), P(states), P(leaf), P(starts), byref(n_evicted), byref(counter),
+                                                   nv.current_stream()))
+        return starts.tolist(), int(n_evicted.value), int(counter.value)
+
     def sample_indices(self, u: torch.Tensor) -> torch.Tensor:
         leaf = torch.empty(u.numel(), dtype=torch.int64, device=self.device)
         nv.check(self.lib.r2d2_replay_sample(self._h, nv.dptr(u), u.numel(), nv.dptr(leaf, torch.int64), None, None,
@@ -271,6 +305,10 @@ class DeviceReplay:
 
     def sample_into(self, eng: LearnerEngine, generator: torch.Generator | None = None, u: torch.Tensor | None = None):
         """Draw eng.cfg.batch starts and gather the time-major batch straight into the engine's buffers."""
+        ec, rc = eng.cfg, self.cfg
+        if (ec.obs, ec.act, ec.hidden, ec.rows) != (rc.obs, rc.act, rc.hidden, rc.rows):
+            raise nv.NativeError("replay shard (obs %d act %d hidden %d rows %d) does not match the engine (obs %d act %d "
+                                 "hidden %d rows %d)" % (rc.obs, rc.act, rc.hidden, rc.rows, ec.obs, ec.act, ec.hidden, ec.rows))
         if u is None:
             eng.uniforms.copy_(torch.rand(eng.cfg.batch, device=self.device, generator=generator))
         else:

@@ -170,23 +170,49 @@ class LearnerReplayMemory:
                           burn_in=self.burn_in_length, learning=self.learning_length, n_step=self.n_step)
 
     def _ensure_device(self, obs_size, n_actions, hidden):
+        """Create the HBM shard on first use.  Sizes given to the constructor are binding: an actor file of another
+        width is an error, not a silent re-shape (the engine's batch buffers are sized from the same numbers)."""
+        for name, want, got in (("obs_size", self._obs, obs_size), ("n_actions", self._act, n_actions),
+                                ("hidden", self._hidden, hidden)):
+            if want is not None and want != got:
+                raise ValueError("actor file %s = %d, learner was built for %d" % (name, got, want))
         if self._dev is None:
             from r2d2_b200.engine import DeviceReplay
             self._obs, self._act, self._hidden = obs_size, n_actions, hidden
-            rows = self._capacity_rows or int(min(self.memory_sequence_size, 2_000_000) * 1.3) + 4096
+            rows = self._capacity_rows or self._default_capacity_rows(obs_size, n_actions, hidden)
             self._dev = DeviceReplay(self._cfg(), capacity_rows=rows, max_sequences=self.memory_sequence_size,
                                      device=self._device)
         return self._dev
 
-    def add_episode(self, rows, states, priority):
-        obs, act, rew, term, st = pack_episode(rows, states)
-        dev = self._ensure_device(obs.shape[1], act.shape[1], st.shape[3])
-        dev.add_episode(obs, act, rew, term, st, np.asarray(priority, np.float32))
-        stats = dev.stats()
-        while len(self._episodes) + 1 > stats["n_episodes"]:   # native FIFO eviction happened
+    def _default_capacity_rows(self, obs_size, n_actions, hidden):
+        """Ring rows for `memory_sequence_size` sequences (one stored row per sequence start plus the 64 rows per
+        episode that start no sequence: x1.3), capped at 60 % of the free HBM.  The reference keeps up to
+        memory_sequence_size sequences in host RAM (replay_memory.py:148); when the cap applies, FIFO eviction starts
+        earlier than there - said out loud, and documented in INTEGRATION.md."""
+        want = int(self.memory_sequence_size * 1.3) + 4096
+        bytes_per_row = 4 * (obs_size + n_actions + 2 + 8 * hidden) + 5      # rows + leaf + ancestors
+        free = torch.cuda.mem_get_info(self._device)[0] if torch.cuda.is_available() else 0
+        fit = int(0.6 * free / bytes_per_row)
+        if 0 < fit < want:
+            print("LearnerReplayMemory: ring capped at %d rows (%.1f GB of HBM) for memory_sequence_size=%d; FIFO "
+                  "eviction starts earlier than the reference's" % (fit, fit * bytes_per_row / 1e9, self.memory_sequence_size))
+            return fit
+        return want
+
+    def _register(self, starts, n_rows, n_starts, n_evicted, counter):
+        """Mirror of the native FIFO: evictions (ring overlap while appending, sequence cap afterwards) always take the
+        oldest episode, so the survivors are (old + new) minus the first `n_evicted`."""
+        for st, nr, ns in zip(starts, n_rows, n_starts):
+            self._episodes.append((int(st), int(nr), int(ns)))
+        for _ in range(min(int(n_evicted), len(self._episodes))):
             self._episodes.popleft()
-        self._episodes.append((int(stats["last_row_start"]), obs.shape[0], len(priority)))
-        self.sequence_counter = int(stats["sequence_counter"])
+        self.sequence_counter = int(counter)
+
+    def add_episode(self, rows, states, priority):
+        obs, act, rew, term, st = pack_episode(rows, states, self._hidden)
+        dev = self._ensure_device(obs.shape[1], act.shape[1], st.shape[3])
+        starts, n_evicted, counter = dev.add_episodes([(obs, act, rew, term, st, np.asarray(priority, np.float32))])
+        self._register(starts, [obs.shape[0]], [len(priority)], n_evicted, counter)
 
     def get_weighted_sample_index(self):
         """Iterator of `batch_size` episode indices drawn proportionally to the episode totals
@@ -216,23 +242,46 @@ class LearnerReplayMemory:
                 states[0], states[1], states[2], states[3])
 
     def load(self, actorID):
-        """Ingest memory{actorID}.pt and hand the file back emptied (replay_memory.py:138-157); one retry after
-        a pause like the reference (replay_memory.py:158-175).  weights_only=False: the payload is a pickle of
-        deques / ndarrays, which torch >= 2.6 refuses by default."""
+        """Ingest memory{actorID}.pt (replay_memory.py:138-157): all episodes of the file are appended, then the oldest
+        are dropped while the sequence counter exceeds memory_sequence_size.
+
+        Differences from the reference, deliberate: (1) the file is CLAIMED by an atomic rename before it is read and
+        removed afterwards (the reference reads it, then rewrites it emptied: an actor's fresh file saved in between is
+        overwritten and its episodes are lost; an emptied file and no file are the same to `learner.py:70-73`, which tests
+        `isfile` first); (2) the whole payload is parsed and validated BEFORE anything is ingested and goes to the
+        device in one native call - a failure cannot leave half a file in the shard, so the reference's retry (one
+        more attempt after a pause, replay_memory.py:158-175) never duplicates episodes; malformed episodes are skipped;
+        (3) weights_only=False: the payload is a pickle of deques / ndarrays, which torch >= 2.6 refuses by default."""
         fname = self.path + 'memory{}.pt'.format(actorID)
         if not os.path.isfile(fname):
             return
+        claimed = fname + '.ingest{}'.format(os.getpid())
+        try:
+            os.replace(fname, claimed)
+        except OSError:
+            return                                          # another process took it, or the actor is mid-rename
+        payload = None
         for attempt in (0, 1):
             try:
-                payload = torch.load(fname, weights_only=False)
-                for rows, states, prio in zip(payload['replay_memory'], payload['recurrent_state'], payload['priority']):
-                    if len(rows) >= self.sequence_length + self.n_step:
-                        self.add_episode(rows, states, prio)
-                for key in ('replay_memory', 'recurrent_state', 'priority', 'total_priority'):
-                    payload[key].clear()
-                torch.save(payload, fname)
-                return
+                payload = torch.load(claimed, weights_only=False)
+                break
             except Exception:
                 if attempt:
+                    os.replace(claimed, fname)              # hand the file back untouched
                     raise
                 sleep(np.random.rand() * 5 + 2)
+        episodes = []
+        for rows, states, prio in zip(payload['replay_memory'], payload['recurrent_state'], payload['priority']):
+            if len(rows) < self.sequence_length + self.n_step:
+                continue
+            try:
+                obs, act, rew, term, st = pack_episode(rows, states, self._hidden)
+            except (ValueError, TypeError, IndexError) as exc:
+                print("LearnerReplayMemory.load: skipping a malformed episode of {}: {}".format(fname, exc))
+                continue
+            episodes.append((obs, act, rew, term, st, np.asarray(prio, np.float32)))
+        if episodes:
+            dev = self._ensure_device(episodes[0][0].shape[1], episodes[0][1].shape[1], episodes[0][4].shape[3])
+            starts, n_evicted, counter = dev.add_episodes(episodes)
+            self._register(starts, [e[0].shape[0] for e in episodes], [len(e[5]) for e in episodes], n_evicted, counter)
+        os.remove(claimed)

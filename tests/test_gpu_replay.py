@@ -1,6 +1,8 @@
 """GPU replay shard: sum-tree indices bit-exact against the C restatement (oracle/sumtree_oracle.c),
 gather correctness, duplicate handling, eviction, and the sampling distribution against the reference's
 two-level sampler (fixture tests/golden/ref_sampler_hist.npz)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -181,3 +183,64 @@ def test_large_tree_bit_exact(eng_mod):
     u = rng.uniform(size=100000).astype(np.float32)
     assert np.array_equal(rp.sample_indices(torch.as_tensor(u).cuda()).cpu().numpy(), oracle.sample(u))
     assert abs(rp.stats()["total_priority"] - oracle.total) == 0.0
+
+
+def test_ingest_matches_reference_load_sequence(tmp_path, monkeypatch):
+    """Next-row N1: the same sequence of actor files through the drop-in LearnerReplayMemory.load and through the
+    UNMODIFIED reference (fixture tests/golden/ref_ingest.npz, oracle/make_golden.py gen_ingest): sequence_counter -
+    incl. the asymmetric eviction arithmetic of replay_memory.py:147 vs :149 - and the surviving episodes after every
+    file.  The file is consumed (claimed by rename, removed) instead of rewritten empty."""
+    import sys
+    from collections import deque
+    from conftest import load_golden
+    from oracle.make_golden import ingest_file_sequence
+    g = load_golden("ref_ingest.npz")
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("memory_data")
+    sys.modules.pop("replay_memory", None)
+    import replay_memory as dropin_rm
+    mem = dropin_rm.LearnerReplayMemory(memory_sequence_size=int(g["memory_sequence_size"]), batch_size=4,
+                                        obs_size=4, n_actions=2, hidden=8, capacity_rows=4096)
+    for i, (actor_id, eps) in enumerate(ingest_file_sequence()):
+        torch.save({"replay_memory": deque([e[0] for e in eps]), "recurrent_state": deque([e[1] for e in eps]),
+                    "priority": deque([e[2] for e in eps]), "total_priority": [sum(e[2]) for e in eps]},
+                   "memory_data/memory{}.pt".format(actor_id))
+        mem.load(actor_id)
+        assert not os.path.exists("memory_data/memory{}.pt".format(actor_id))
+        assert mem.sequence_counter == int(g["sequence_counter"][i]), f"file {i}"
+        # surviving episodes: the tag stored in obs[0] of each episode's first row, read back from HBM
+        tags = []
+        for (start, n_rows, n_starts) in mem.memory:
+            leaf = torch.tensor([start], dtype=torch.int64, device="cuda")
+            obs = torch.empty((65, 1, 4), device="cuda")
+            from r2d2_b200 import native as nv
+            # gather the window that starts at the episode's first row (explicit leaf, no draw)
+            nv.check(mem._dev.lib.r2d2_replay_gather(mem._dev._h, nv.dptr(leaf, torch.int64), 1, nv.dptr(obs), None, None,
+                                                     None, None, nv.current_stream()))
+            tags.append(int(round(float(obs[0, 0, 0].item()))))
+        assert tags == [int(t) for t in g[f"survivors/{i}"]], f"file {i}"
+    sys.modules.pop("replay_memory", None)
+
+
+def test_ring_wrap_evicts_until_no_overlap(eng_mod):
+    engine = eng_mod
+    """ADVICE r1: oldest episode at the tail of the ring, a younger one at the head that the wrapped episode overwrites:
+    both must be evicted (FIFO), not an error."""
+    cfg = engine.PathConfig(obs=3, act=1, hidden=8, batch=2, burn_in=2, learning=3, n_step=1)   # window = 6 rows
+    rp = engine.DeviceReplay(cfg, capacity_rows=100)
+    rng = np.random.default_rng(0)
+
+    def ep(n):
+        return (rng.standard_normal((n, 3)).astype(np.float32), rng.uniform(-1, 1, (n, 1)).astype(np.float32),
+                rng.standard_normal(n).astype(np.float32), np.zeros(n, np.float32),
+                np.zeros((n - 1, 4, 2, 8), np.float32), rng.uniform(0.1, 1, n - 5).astype(np.float32))
+    rp.add_episodes([ep(60)])            # A @ [0, 60)
+    rp.add_episodes([ep(40)])            # F @ [60, 100)
+    rp.add_episodes([ep(50)])            # G wraps to [0, 50): evicts A
+    st = rp.stats()
+    assert st["n_episodes"] == 2
+    starts, n_evicted, _ = rp.add_episodes([ep(60)])   # does not fit behind G (50 + 60 > 100): wraps to [0, 60) -> F then G go
+    assert starts == [0] and n_evicted == 2
+    assert rp.stats()["n_episodes"] == 1
+    leaves = rp.tree_level(0).cpu().numpy()
+    assert (leaves[60:] == 0).all() and abs(float(rp.tree_level(rp.stats()["tree_levels"] - 1)[0]) - leaves[:55].sum()) < 1e-4
