@@ -246,6 +246,8 @@ int r2d2_learner_actor_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t 
 /* phase 3: actor Adam, step counter, hard target update every target_update_interval steps */
 int r2d2_learner_finish_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t stream);
 int r2d2_learner_step_count(r2d2_learner_t* l);
+/* resume: completed iterations so far (drives Adam's bias correction and the target-update period, learner.py:82,131) */
+int r2d2_learner_set_step_count(r2d2_learner_t* l, int step);
 /* number of kernels launched by the three phases of one iteration (bench.py's gpu_launches) */
 int r2d2_learner_launches_per_iteration(r2d2_learner_t* l);
 

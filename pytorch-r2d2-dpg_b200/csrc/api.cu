@@ -228,6 +228,11 @@ int r2d2_learner_finish_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t
   return learner_finish_phase(reinterpret_cast<Learner*>(l), grad_scale, S(stream));
 }
 int r2d2_learner_step_count(r2d2_learner_t* l) { return l ? reinterpret_cast<Learner*>(l)->step : -1; }
+int r2d2_learner_set_step_count(r2d2_learner_t* l, int step) {
+  R2D2_REQUIRE(l && step >= 0, "step");
+  reinterpret_cast<Learner*>(l)->step = step;
+  return R2D2_OK;
+}
 int r2d2_learner_launches_per_iteration(r2d2_learner_t* lh) {
   if (!lh) return -1;
   Learner* l = reinterpret_cast<Learner*>(lh);

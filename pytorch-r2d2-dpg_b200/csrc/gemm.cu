@@ -262,8 +262,11 @@ bool gemm_supports_bias2(int M, int N, int K) {
   return gemm_get_impl() == 1 && !(skinny && gemm_get_impl_skinny_mma());
 }
 
-bool gemm_emits_operand_image(int N, int K_total) {
-  return gemm_get_impl() == 1 && gemm_get_impl_skinny_mma() && K_total <= 32 && N > 32 && N % 32 == 0;
+bool gemm_emits_operand_image(int M, int N, int K_total) {
+  if (gemm_get_impl() != 1 || N <= 32 || N % 32 != 0) return false;
+  if (gemm_get_impl_skinny_mma() && K_total <= 32) return true;                 // small-K streaming kernel (gemm_thin.cu)
+  const bool skinny = (K_total < 64) || (M < 32);
+  return !(skinny && gemm_get_impl_skinny_mma());                              // tcgen05 epilogue (gemm_tc.cu)
 }
 
 int gemm_suggest_split_k(int M, int N, int K) {
@@ -315,7 +318,8 @@ static int gemm_f32_dispatch(const GemmParams& p, GemmLayout layout, cudaStream_
     if (handled) { *colsums_done = true; return R2D2_OK; }
   }
   R2D2_REQUIRE(!p.bias2 || gemm_supports_bias2(p.M, p.N, p.K + p.K2), "bias2 needs the tcgen05 path (gemm_supports_bias2)");
-  R2D2_REQUIRE(!p.C_img_k && !p.C_img_mn, "C_img_* is only produced by the small-K streaming kernel (see gemm_emits_operand_image)");
+  R2D2_REQUIRE((!p.C_img_k && !p.C_img_mn) || (layout == GEMM_NT && gemm_emits_operand_image(p.M, p.N, p.K + p.K2)),
+               "C_img_* is produced by the small-K streaming kernel and the tcgen05 epilogue only (see gemm_emits_operand_image)");
   if (gemm_get_impl() == 1 && !(skinny && gemm_get_impl_skinny_mma())) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("R2D2_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }

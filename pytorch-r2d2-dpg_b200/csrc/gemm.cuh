@@ -36,7 +36,7 @@ struct GemmParams {
   int split_k = 1;           // >1: partial products are atomically added into C (C must be pre-zeroed)
   const unsigned char* A_img = nullptr;   // tcgen05 path: A already in packed tile-major form (gemm_tc.cu image of this
                              // call's layout and tiling, e.g. written by the BPTT scan); A / lda are ignored
-  unsigned char* C_img_k = nullptr;      // small-K kernel only (gemm_thin.cu): also write C as the K-major packed operand image
+  unsigned char* C_img_k = nullptr;      // NT, N % 32 == 0 (gemm_emits_operand_image): also write C as the K-major packed operand image
                              // [ceil(M/128)][N/32][16 KB] for a following product that contracts over N
   unsigned char* C_img_mn = nullptr;     // same, MN-major image [ceil(N/128)][ceil(M/32)][16 KB]: C as the B operand of a TN
                              // product that contracts over C's rows (z1 in dW_ih)
@@ -49,8 +49,9 @@ struct GemmParams {
 };
 
 int gemm_f32(const GemmParams& p, GemmLayout layout, cudaStream_t stream);
-// true when gemm_f32 will honour GemmParams::C_img_k for an NT product with these sizes (small-K streaming kernel selected)
-bool gemm_emits_operand_image(int N, int K_total);
+// true when gemm_f32 will honour GemmParams::C_img_k / C_img_mn for an NT product with these sizes (the small-K streaming
+// kernel or the tcgen05 epilogue is selected)
+bool gemm_emits_operand_image(int M, int N, int K_total);
 // true when gemm_f32 will take this NT product on the tcgen05 path, which honours GemmParams::bias2
 bool gemm_supports_bias2(int M, int N, int K);
 // picks a split-K factor so that a skinny-output wgrad GEMM fills the 148 SMs

@@ -98,6 +98,8 @@ struct PackedGemmParams {
   int epilogue, split_k;
   int a_mn, b_mn;            // operand majors (1 = MN-major)
   int debug_flags;
+  unsigned char* c_img_k;    // optional: C also leaves as packed operand images (N % 32 == 0, split_k == 1), see epilogue
+  unsigned char* c_img_mn;
 };
 
 template <int NBT>
@@ -239,10 +241,48 @@ __global__ void __launch_bounds__(PACKED_GEMM_THREADS, 2) gemm_packed_kernel(Pac
           for (int j = 0; j < 4; ++j) if (j < nv) bv[j] += __ldg(p.bias2 + col + j);
         }
       }
+      const bool img = p.c_img_k != nullptr || p.c_img_mn != nullptr;   // kernel-uniform
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + rr, row = m0 + q * 32 + r;
-        if (!live || row >= p.M) continue;
+        if (!img && (!live || row >= p.M)) continue;
+        if (img) {
+          // C also leaves as the bf16 hi/lo operand image(s) of the product(s) that consume it next (tile format at the
+          // top of this file): a 16-byte piece = 8 consecutive columns of one row; lanes cc / cc^1 hold its two halves.
+          // Every lane takes part in the shuffles; rows >= M are written as zeros (a reduction index in the MN-major image).
+          const bool ok = live && row < p.M;
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (ok) {
+            const float4 a = *reinterpret_cast<const float4*>(&stg[r * SLD + cc * 4]);
+            v[0] = a.x + bv[0]; v[1] = a.y + bv[1]; v[2] = a.z + bv[2]; v[3] = a.w + bv[3];
+            if (p.epilogue == EPI_TANH) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = tanhf(v[j]);
+            }
+            *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          uint32_t h0, h1, l0, l1;
+          split_pack2(v[0], v[1], h0, l0);
+          split_pack2(v[2], v[3], h1, l1);
+          const uint32_t ph0 = __shfl_xor_sync(0xffffffffu, h0, 1), ph1 = __shfl_xor_sync(0xffffffffu, h1, 1);
+          const uint32_t pl0 = __shfl_xor_sync(0xffffffffu, l0, 1), pl1 = __shfl_xor_sync(0xffffffffu, l1, 1);
+          if ((cc & 1) == 0 && (c0 + cc * 4 < c_end) && col < p.N && row < ((p.M + 31) & ~31)) {
+            const uint4 hi = make_uint4(h0, h1, ph0, ph1), lo = make_uint4(l0, l1, pl0, pl1);
+            if (p.c_img_k && row < p.M) {
+              unsigned char* d = p.c_img_k + ((size_t)(row >> 7) * (p.N >> 5) + (col >> 5)) * TILE_BYTES +
+                                 ((((row & 127) >> 3) * 32) + ((col & 31) >> 3) * 8 + (row & 7)) * 16;
+              *reinterpret_cast<uint4*>(d) = hi;
+              *reinterpret_cast<uint4*>(d + PLANE_BYTES) = lo;
+            }
+            if (p.c_img_mn) {
+              unsigned char* d = p.c_img_mn + ((size_t)(col >> 7) * ((p.M + 31) >> 5) + (row >> 5)) * TILE_BYTES +
+                                 ((((row & 31) >> 3) * 128) + ((col & 127) >> 3) * 8 + (row & 7)) * 16;
+              *reinterpret_cast<uint4*>(d) = hi;
+              *reinterpret_cast<uint4*>(d + PLANE_BYTES) = lo;
+            }
+          }
+          continue;
+        }
         const float4 a = *reinterpret_cast<const float4*>(&stg[r * SLD + cc * 4]);
         float v[4] = {a.x + bv[0], a.y + bv[1], a.z + bv[2], a.w + bv[3]};
         if (p.epilogue == EPI_TANH) {
@@ -367,6 +407,12 @@ int gemm_f32_tc(const GemmParams& p, GemmLayout layout, cudaStream_t stream) {
   q.pa = p.A_img ? p.A_img : g_pack_a.ptr; q.pb = p.B_img ? p.B_img : g_pack_b.ptr; q.k_tiles = k_tiles; q.C = p.C; q.ldc = p.ldc; q.M = p.M; q.N = p.N;
   q.bias = p.bias; q.bias2 = p.bias ? p.bias2 : nullptr; q.Z = p.Z; q.ldz = p.ldz; q.epilogue = p.epilogue; q.split_k = p.split_k;
   q.a_mn = a_mn; q.b_mn = b_mn; q.debug_flags = p.debug_flags;
+  q.c_img_k = p.C_img_k; q.c_img_mn = p.C_img_mn;
+  if (p.C_img_k || p.C_img_mn) {
+    R2D2_REQUIRE(p.N % 32 == 0 && p.split_k == 1 && (p.epilogue == EPI_NONE || p.epilogue == EPI_TANH) &&
+                     (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0,
+                 "operand image from the tcgen05 epilogue: N % 32 == 0, no split-K, bias / tanh epilogue, 16-byte aligned C");
+  }
   static int force_nbt = -1;
   if (force_nbt < 0) { const char* e = getenv("R2D2_GEMM_NBT"); force_nbt = e ? atoi(e) : 0; }
   // two B tiles per CTA when the A images would otherwise be re-read many times (N >= 512) or the CTA count is set by

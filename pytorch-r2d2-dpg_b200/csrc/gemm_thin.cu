@@ -259,6 +259,72 @@ __global__ void __launch_bounds__(SN_THREADS) thin_smalln_kernel(GemmParams p, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small-N products whose K is 128 / 256 / 512 (the heads at H = 128..512: N = 1..32 outputs per row).  The kernel
+// above keeps 32 accumulators per lane and re-reads the whole [NP][K] weight tile from shared memory for every ROW
+// (64 KB of shared-memory traffic per row at K = 512: it ran at the shared-memory roof, 104 us for the 64000 x 17 x 512
+// head of cfg-3).  Here a warp owns FOUR rows: lane = 8 * row + j, lane j of a row loads the 16-byte pieces
+// j, j + 8, j + 16, ... of that row (the 8 lanes of a row read 128 contiguous bytes per instruction, 4 full lines per
+// warp instruction) and keeps them in registers; for every output column the 8 lanes of a row multiply their pieces
+// with the matching weight pieces (shared memory: 8 distinct 16-byte addresses per instruction, broadcast over the
+// rows) and a 3-step shuffle tree adds the 8 partial sums.
+// ------------------------------------------------------------------------------------------------
+template <bool NN, int KI>   // KI = K / 32: float4 pieces per lane
+__global__ void __launch_bounds__(256) thin_rowdot_kernel(GemmParams p) {
+  extern __shared__ __align__(16) float Wt[];   // [N][K]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = KI * 32;
+  for (int idx = tid; idx < p.N * K; idx += 256) {
+    int n, k;
+    if (NN) { k = idx / p.N; n = idx % p.N; } else { n = idx / K; k = idx % K; }
+    Wt[n * K + k] = NN ? __ldg(p.B + (long long)k * p.ldb + n) : __ldg(p.B + (long long)n * p.ldb + k);
+  }
+  __syncthreads();
+  const int j = lane & 7, r = lane >> 3;
+  const bool needs_z = p.epilogue == EPI_MUL_DTANH || p.epilogue == EPI_ADD_Z;
+  const int groups = (p.M + 3) >> 2;
+  for (int g = blockIdx.x * 8 + warp; g < groups; g += gridDim.x * 8) {
+    const int row = g * 4 + r;
+    const bool on = row < p.M;
+    float4 a[KI];
+    const float4* arow = reinterpret_cast<const float4*>(p.A + (long long)(on ? row : 0) * p.lda);
+#pragma unroll
+    for (int i = 0; i < KI; ++i) a[i] = on ? __ldg(arow + i * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < p.N; ++n) {
+      const float4* wrow = reinterpret_cast<const float4*>(Wt + n * K);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < KI; ++i) {
+        const float4 w = wrow[i * 8 + j];
+        acc = fmaf(a[i].w, w.w, fmaf(a[i].z, w.z, fmaf(a[i].y, w.y, fmaf(a[i].x, w.x, acc))));
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (on && (n & 7) == j) {   // the 8 lanes of a row share the stores
+        const float b = p.bias ? __ldg(p.bias + n) : 0.f;
+        const float z = needs_z ? p.Z[(long long)row * p.ldz + n] : 0.f;
+        p.C[(long long)row * p.ldc + n] = apply_epilogue(acc + b, p.epilogue, z);
+      }
+    }
+  }
+}
+
+template <bool NN, int KI>
+int launch_thin_rowdot(const GemmParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t)p.N * KI * 32 * sizeof(float);
+  static PerDeviceOnce once;
+  if (smem > 48 * 1024 && once.need())
+    R2D2_CUDA_TRY(cudaFuncSetAttribute(thin_rowdot_kernel<NN, KI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  const int groups = ceil_div(p.M, 4);
+  int grid = ceil_div(groups, 8);
+  if (grid > 148 * 4) grid = 148 * 4;
+  thin_rowdot_kernel<NN, KI><<<grid, 256, smem, stream>>>(p);
+  count_launch();
+  R2D2_CUDA_TRY(cudaGetLastError());
+  return R2D2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // TN with one small output dimension: X[K rows][P] is the wide operand (thread = one of its columns), Y[K rows][Q<=32]
 // the narrow one (staged per 32-row chunk in shared memory, read as broadcast float4).  X rows are fetched sixteen at a
 // time (the kernel is latency bound otherwise).  Accumulates into C with atomics once per block (split-K contract
@@ -390,6 +456,13 @@ int gemm_thin_try(const GemmParams& p, GemmLayout layout, cudaStream_t stream, b
   }
   if (p.split_k != 1) return R2D2_OK;
   const bool nn = layout == GEMM_NN;
+  if (p.N <= 32 && p.K2 == 0 && (p.K == 128 || p.K == 256 || p.K == 512) && aligned16(p.A, p.lda) &&
+      (size_t)p.N * p.K * sizeof(float) <= 64 * 1024) {
+    *handled = true;
+    if (p.K == 128) return nn ? launch_thin_rowdot<true, 4>(p, stream) : launch_thin_rowdot<false, 4>(p, stream);
+    if (p.K == 256) return nn ? launch_thin_rowdot<true, 8>(p, stream) : launch_thin_rowdot<false, 8>(p, stream);
+    return nn ? launch_thin_rowdot<true, 16>(p, stream) : launch_thin_rowdot<false, 16>(p, stream);
+  }
   if (p.N <= 32 && p.K2 == 0 && p.K >= 64 && p.K <= 2048 && (p.K % 4 == 0) && aligned16(p.A, p.lda)) {
     *handled = true;
     if (p.N <= 8)  return nn ? launch_thin_smalln<true, 8>(p, stream) : launch_thin_smalln<false, 8>(p, stream);

@@ -74,7 +74,7 @@ int net_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, const 
     g.C = ws.z1; g.ldc = H; g.M = M; g.N = H; g.bias = P.b1; g.epilogue = EPI_TANH;
     // the l1 kernel can write z1 a second time as the packed A operand of the W_ih product (the BPTT image buffer is
     // idle during the forward pass)
-    z1_img = ws.img_k != nullptr && gemm_emits_operand_image(H, I);
+    z1_img = ws.img_k != nullptr && gemm_emits_operand_image(M, H, I);
     if (z1_img) g.C_img_k = ws.img_k;
     if (z1_img && ws.keep_z1_image && ws.img_z_mn) {   // second copy as the B operand of dW_ih (BPTT of this chain)
       g.C_img_mn = ws.img_z_mn;
@@ -170,7 +170,7 @@ int net_backward(const NetShape& s, const NetParams& P, const NetParams* G, cons
       GemmParams g;
       g.A = dgin; g.lda = 4 * H; g.B = ws.z1; g.ldb = H; g.K = M;
       if (use_img) g.A_img = ws.img_mn_gin;
-      if (use_img && ws.keep_z1_image && ws.img_z_mn && gemm_emits_operand_image(H, I)) g.B_img = ws.img_z_mn;
+      if (use_img && ws.keep_z1_image && ws.img_z_mn && gemm_emits_operand_image(M, H, I)) g.B_img = ws.img_z_mn;
       g.C = G->wih; g.ldc = H; g.M = 4 * H; g.N = H; g.split_k = gemm_suggest_split_k(4 * H, H, M);
       g.reuse_packed_a = (repeat == 1);   // same dG operand as the dW_hh product just above
       R2D2_TRY(gemm_f32(g, GEMM_TN, stream));

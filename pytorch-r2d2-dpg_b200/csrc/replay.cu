@@ -67,21 +67,25 @@ __device__ __forceinline__ float node_sum(const float* __restrict__ children) {
 }
 
 // single CTA: write the batch's leaves (highest batch index wins on duplicates, learner.py:136-139
-// executes the writes in batch order), then refresh every ancestor level by level.
+// executes the writes in batch order), then refresh every ancestor level by level.  The leaf indices sit in shared
+// memory: the last-writer test is a broadcast scan of the later entries (B^2 / 2 shared reads instead of global ones).
 __global__ void __launch_bounds__(1024) tree_update_kernel(TreeView tv, const long long* __restrict__ leaf,
                                                            const float* __restrict__ prio, int batch) {
+  extern __shared__ long long s_leaf[];
+  for (int i = threadIdx.x; i < batch; i += blockDim.x) s_leaf[i] = leaf[i];
+  __syncthreads();
   for (int i = threadIdx.x; i < batch; i += blockDim.x) {
-    const long long li = leaf[i];
+    const long long li = s_leaf[i];
     bool winner = true;
     for (int j = i + 1; j < batch; ++j)
-      if (leaf[j] == li) { winner = false; break; }
+      if (s_leaf[j] == li) { winner = false; break; }
     if (winner) tv.lvl[0][li] = prio[i];
   }
   __syncthreads();
   long long div = TREE_K;
   for (int l = 1; l < tv.levels; ++l) {
     for (int i = threadIdx.x; i < batch; i += blockDim.x) {
-      const long long node = leaf[i] / div;
+      const long long node = s_leaf[i] / div;
       tv.lvl[l][node] = node_sum(tv.lvl[l - 1] + node * TREE_K);
     }
     __syncthreads();
@@ -422,7 +426,8 @@ int replay_sample(Replay* r, const float* u, int batch, long long* leaf_idx, flo
 
 int replay_update_priorities(Replay* r, const long long* leaf_idx, const float* prio, int batch, cudaStream_t stream) {
   R2D2_REQUIRE(r && leaf_idx && prio && batch > 0, "args");
-  tree_update_kernel<<<1, 1024, 0, stream>>>(r->tv, leaf_idx, prio, batch);
+  R2D2_REQUIRE(batch <= 5120, "priority batch larger than the shared-memory index table (40 KB)");
+  tree_update_kernel<<<1, 1024, sizeof(long long) * (size_t)batch, stream>>>(r->tv, leaf_idx, prio, batch);
   count_launch();
   R2D2_CUDA_TRY(cudaGetLastError());
   return R2D2_OK;

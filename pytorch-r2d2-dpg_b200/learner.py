@@ -78,7 +78,22 @@ class Learner:
         self.memory = LearnerReplayMemory(memory_sequence_size=self.memory_sequence_size, batch_size=self.batch_size,
                                           obs_size=self.obs_size, n_actions=self.n_actions, hidden=self.hidden,
                                           device=self.engine.device)
+        self.state_path = self.model_path + 'learner_state.pt'
+        if os.environ.get("R2D2_RESUME", "0") == "1" and os.path.isfile(self.state_path):
+            self.load_checkpoint()                         # every rank loads the same file: replicas stay identical
         self.save_model()
+
+    def save_checkpoint(self):
+        """Resumable state next to model.pt: nets + both Adam moment sets + step counter (the reference's model.pt has
+        weights only, learner.py:56-61, and its learner never loads).  model.pt keeps the reference's format for actors."""
+        if not self.dist_env.is_main:
+            return
+        tmp = self.state_path + '.tmp{}'.format(os.getpid())
+        torch.save(self.engine.training_state(), tmp)
+        os.replace(tmp, self.state_path)
+
+    def load_checkpoint(self):
+        self.engine.load_training_state(torch.load(self.state_path, map_location="cpu"))
 
     # the four nets as state_dict-compatible views of the engine's flat parameter blocks
     def _sd(self, net):
@@ -120,6 +135,8 @@ class Learner:
             dev.update_priorities(self.engine.leaf_idx, self.engine.priority)   # learner.py:135-139
             if step % self.model_save_interval == 0:
                 self.save_model()
+                if os.environ.get("R2D2_SAVE_STATE", "1") == "1":
+                    self.save_checkpoint()
             if step % self.memory_update_interval == 0:
                 self._ingest()                                         # learner.py:144-149 without the sleep stall
         torch.cuda.synchronize()

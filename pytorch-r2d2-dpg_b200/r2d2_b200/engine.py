@@ -221,6 +221,27 @@ class LearnerEngine:
     def step_count(self) -> int:
         return int(self.lib.r2d2_learner_step_count(self._h))
 
+    # ---- full training state (the reference checkpoints weights only and cannot resume) ---------------
+    def training_state(self) -> dict:
+        """Everything a restart needs: the four nets (reference keys), both Adam moment sets, the step counter."""
+        torch.cuda.synchronize(self.device)
+        out = {net: self.state_dict(net) for net in ("actor", "target_actor", "critic", "target_critic")}
+        for net in ("actor", "critic"):
+            out[net + "_optimizer"] = {"exp_avg": OrderedDict((k, v.detach().clone()) for k, v in self.views(net, "exp_avg").items()),
+                                       "exp_avg_sq": OrderedDict((k, v.detach().clone()) for k, v in self.views(net, "exp_avg_sq").items())}
+        out["step"] = self.step_count
+        return out
+
+    def load_training_state(self, st: dict):
+        self.load_state_dicts(st["actor"], st["critic"], st.get("target_actor"), st.get("target_critic"))
+        for net in ("actor", "critic"):
+            opt = st.get(net + "_optimizer")
+            if opt is not None:
+                for what in ("exp_avg", "exp_avg_sq"):
+                    for k, v in self.views(net, what).items():
+                        v.copy_(torch.as_tensor(opt[what][k], dtype=torch.float32).to(self.device))
+        nv.check(self.lib.r2d2_learner_set_step_count(self._h, int(st.get("step", 0))))
+
     @property
     def launches_per_iteration(self) -> int:
         return int(self.lib.r2d2_learner_launches_per_iteration(self._h))

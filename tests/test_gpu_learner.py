@@ -220,3 +220,32 @@ def test_edge_shapes_against_port(eng_mod, obs, act, hidden, batch, burn_in, lea
                 errs[f"{net}_after/{k}"] = rel_l2(pa[k], ref[f"{net}_after"][k])
         bad = {k: v for k, v in errs.items() if not v < TOL}
         assert not bad, f"iteration {it}: {bad}"
+
+
+def test_training_state_resume_continues_the_run(eng_mod):
+    """Next-row N3: nets + Adam moments + step counter round-trip; an engine restored from the state after 2 iterations
+    continues like the one that never stopped (Adam bias correction and the target period depend on the step; the
+    comparison allows for the run-to-run rounding of the split-K reductions, nothing more)."""
+    pc = ref_port.PathConfig(obs=6, act=2, hidden=64, batch=8, burn_in=4, learning=6, n_step=2, target_interval=3)
+    cfg = eng_mod.PathConfig(obs=6, act=2, hidden=64, batch=8, burn_in=4, learning=6, n_step=2, target_interval=3)
+    a = eng_mod.LearnerEngine(cfg, seed=9)
+    for it in range(2):
+        a.set_batch(ref_port.synthetic_batch(pc, seed=it))
+        a.step()
+    st = a.training_state()
+    assert st["step"] == 2 and set(st) >= {"actor", "critic", "target_actor", "target_critic", "actor_optimizer", "critic_optimizer"}
+    b = eng_mod.LearnerEngine(cfg, seed=123)          # different initial weights: everything must come from the state
+    b.load_training_state(st)
+    assert b.step_count == 2
+    for it in range(2, 5):                             # crosses a hard target update (step 3)
+        batch = ref_port.synthetic_batch(pc, seed=it)
+        for e in (a, b):
+            e.set_batch(batch)
+            e.step()
+    torch.cuda.synchronize()
+    for net in ("actor", "critic", "target_actor", "target_critic"):
+        assert rel_l2(a.flat[net].cpu().numpy(), b.flat[net].cpu().numpy()) < 1e-5, net
+    for net in ("actor", "critic"):
+        assert rel_l2(a.exp_avg[net].cpu().numpy(), b.exp_avg[net].cpu().numpy()) < 1e-4
+        assert rel_l2(a.exp_avg_sq[net].cpu().numpy(), b.exp_avg_sq[net].cpu().numpy()) < 1e-4
+    assert torch.equal(a.flat["target_critic"], a.flat["critic"]) == torch.equal(b.flat["target_critic"], b.flat["critic"])
