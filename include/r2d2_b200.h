@@ -95,6 +95,10 @@ int r2d2_lstm_scan_backward(const float* gates, const float* hs, const float* cs
 /* debug: forward scan that also records per-step globaltimer stamps [grid][S][8] (thread 0 of every CTA) */
 int r2d2_debug_scan_forward_trace(const float* gin, const float* whh, float* gates, float* hs, float* cs, int T, int B,
                                   int H, long long* trace, r2d2_stream_t stream);
+/* debug: BPTT scan (H = 512 kernel) that also records per-step globaltimer stamps [grid][S][8] */
+int r2d2_debug_scan_backward_trace(const float* gates, const float* hs, const float* cs, const float* whh,
+                                   const float* dh_head, float* dgates, int T, int B, int H, long long* trace,
+                                   r2d2_stream_t stream);
 /* debug: clusters of the tcgen05 scan kernel the device can keep resident at once (-1 if not instantiated) */
 int r2d2_debug_max_active_clusters(int H, int nb, int backward);
 /* GEMM implementation switch for A/B checks: 1 = tcgen05/TMEM with skinny problems (K<64, N<32 or M<32) on the

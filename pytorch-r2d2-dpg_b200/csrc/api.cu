@@ -119,6 +119,15 @@ int r2d2_debug_scan_forward_trace(const float* gin, const float* whh, float* gat
   return lstm_scan_forward(p, S(stream));
 }
 
+int r2d2_debug_scan_backward_trace(const float* gates, const float* hs, const float* cs, const float* whh,
+                                   const float* dh_head, float* dgates, int T, int B, int H, long long* trace,
+                                   r2d2_stream_t stream) {
+  ScanBwdParams p;
+  p.gates = gates; p.hs = hs; p.cs = cs; p.whh = whh; p.dh_head = dh_head; p.dgates = dgates; p.dgin = dgates;
+  p.T = T; p.B = B; p.H = H; p.repeat = 1; p.trace = trace;
+  return lstm_scan_backward(p, S(stream));
+}
+
 int r2d2_debug_max_active_clusters(int H, int nb, int backward) { return lstm_scan_max_active_clusters(H, nb, backward); }
 
 int r2d2_set_gemm_impl(int impl) {

@@ -50,6 +50,8 @@ struct ScanBwdParams {
   int rows_per_cluster = 0;        // set by the tcgen05 dispatcher
   unsigned char* xchg = nullptr;   // set by the tcgen05 dispatcher (H = 512): global scratch of the partial-sum exchange through L2
   int dbg = 0;                     // dev only (env R2D2_SCAN_DBG): 1 = skip the dG stores, 2 = skip the saved-activation loads
+  long long* trace = nullptr;      // debug: [grid][S][8] globaltimer stamps (H = 512 kernel, tools/trace_bwd.py)
+  int row_begin = 0, row_end = 0;  // set by the tcgen05 dispatcher: batch rows [row_begin, row_end) of THIS launch (0, 0 = all)
 };
 
 // true when lstm_scan_backward will honour img_* (persistent tcgen05 kernels selected for this hidden size)

@@ -622,14 +622,16 @@ struct TcBwdSmem {
   static_assert(OFF_WLO % 128 == 0, "descriptor alignment");
 };
 
+#define BWD_STAMP(cond, slot) do { if (SM::BIG && p.trace && (cond)) p.trace[((size_t)blockIdx.x * S + it) * 8 + (slot)] = gtime(); } while (0)
+
 template <int H, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwdParams p, int* err) {
   using SM = TcBwdSmem<H, NB>;
   constexpr int C = SM::C, MT = SM::MT, RG = NB / 8, NT = RG / 2;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int b0 = (blockIdx.x / C) * p.rows_per_cluster;  // this cluster's batch rows [b0, b_end), at most NB of them
-  const int b_end = min(p.B, b0 + p.rows_per_cluster);
+  const int b0 = p.row_begin + (blockIdx.x / C) * p.rows_per_cluster;  // this cluster's batch rows [b0, b_end), at most NB of them
+  const int b_end = min(p.row_end > 0 ? p.row_end : p.B, b0 + p.rows_per_cluster);
   const int n_valid = b_end - b0;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -779,9 +781,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     // cs[s] is c_prev of this step and c_new of the next one, so only one new cell state per step.
     float ng[NT][4], nc[NT], nh[NT];
     fetch(ng, nc, nh, s > 0);   // (issuing these behind the proxy fence below instead was measured SLOWER: 11.7 -> 12.7 us per step)
+    BWD_STAMP(tid == 0, 0);
     if (it > 0 && !*dead) {
       if (!tc::mbar_wait(&ps_full[buf], ((it - 1) >> 1) & 1)) { *dead = 1; atomicExch(err, 3); }
     }
+    BWD_STAMP(tid == 0, 1);
 
     const bool emit_gin = p.repeat > 1 && rep == 0;
     // ---- pointwise backward of the cell (thread = (unit = lane, row r8 of row group e)); the dG values go to the MMA
@@ -887,9 +891,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
         }
       }
     };
+    BWD_STAMP(tid == 0, 2);
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
     __syncthreads();
+    BWD_STAMP(tid == 32, 3);   // warp 1: a dependent instruction follows (the barrier itself defers blocking)
     if (s == 0) { store_dg(); break; }  // dh_{-1} is not needed: the initial state is data, not a parameter
     if (SM::BIG && w_u == 1 && lane < C) {   // every thread of this CTA has consumed its receive buffer (phase `it`)
       tc::mbar_arrive_remote_relaxed(ps_free, (uint32_t)lane);   // relaxed: the release form is a MEMBAR.GPU behind this thread's dG stores
@@ -918,6 +924,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       if (!SM::BIG) tc::mma_commit(mma_done);
       }
       __syncwarp();
+      BWD_STAMP(tid == 0, 4);
     }
     if (!(p.dbg & 1)) store_dg();   // HBM copies of dG (and the per-row dgin sums) overlap with the tensor-core step
     if constexpr (SM::BIG) {
@@ -936,6 +943,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       }
       tc::fence_after_thread_sync();
       __syncwarp();
+      BWD_STAMP(tid == 15 * 32, 5);
       float* pst_w = pstage + (size_t)w * NB * 32;
 #pragma unroll
       for (int cb = 0; cb < RG; ++cb) {
@@ -955,9 +963,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
           // through L2 (profiles/r02_xchg_bench.txt): store my partials for owner d, wait for the writes, then a bulk
           // load "multicast" to that single CTA: it lands at the same CTA-relative offset in d and completes d's mbarrier
           unsigned char* g = p.xchg + ((((size_t)(blockIdx.x / C) * 2 + (it & 1)) * C + rank) * C + d) * (size_t)(NB * 128);
+          BWD_STAMP(w_u == 15, 6);
           tc::bulk_store_s2g(g, src, slot_bytes);
           tc::bulk_commit_wait_all();
           tc::bulk_copy_g2s_multicast(dst_local, g, slot_bytes, tc::smem_u32(&ps_full[buf ^ 1]), (uint16_t)(1u << d));
+          BWD_STAMP(w_u == 15, 7);
         } else {
           tc::bulk_copy_to_cluster(tc::mapa(dst_local, d), src, slot_bytes, tc::mapa(tc::smem_u32(&ps_full[buf ^ 1]), d));
         }
@@ -1538,6 +1548,23 @@ int bwd_tc(const ScanBwdParams& p_in, cudaStream_t stream) {
   }
   if (t.nb == 16)
     return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 16>, p, H / 32, t.n_clusters, TcBwdSmem<H, 16>::BYTES, stream);
+  if constexpr (H == 512) {
+    // Waves: only `fit` (7) clusters of 16 are resident and a wave of 32-row clusters costs the same ~3.9 us per step
+    // whether 7 or 2 clusters run in it.  512 rows as 16 clusters = waves of 7 + 7 + 2; instead the full waves run as
+    // 32-row clusters and the remainder as 16-row clusters (shorter MMA and cell phases) in ONE extra wave of a second launch.
+    static int fit32 = -2;
+    if (fit32 == -2) fit32 = max_active_clusters(lstm_scan_bwd_tc_kernel<H, 32>, H / 32, TcBwdSmem<H, 32>::BYTES);
+    const int fit = fit32 > 0 ? fit32 : 7;
+    const int full = (t.n_clusters / fit) * fit;                  // clusters of 32 rows in full waves
+    const int rest_rows = p.B - full * 32;
+    if (t.rows_per_cluster == 32 && full > 0 && rest_rows > 0 && ceil_div(rest_rows, 16) <= fit) {
+      ScanBwdParams a = p, b = p;
+      a.row_begin = 0; a.row_end = full * 32;
+      b.row_begin = full * 32; b.row_end = p.B; b.rows_per_cluster = 16;
+      R2D2_TRY(launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 32>, a, H / 32, full, TcBwdSmem<H, 32>::BYTES, stream));
+      return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 16>, b, H / 32, ceil_div(rest_rows, 16), TcBwdSmem<H, 16>::BYTES, stream);
+    }
+  }
   return launch_cluster_tc(lstm_scan_bwd_tc_kernel<H, 32>, p, H / 32, t.n_clusters, TcBwdSmem<H, 32>::BYTES, stream);
 }
 

@@ -143,6 +143,8 @@ NET_CASES = [
     (20, 4, 512, 40, 4, 2, False, 0),       # three clusters of 16 rows (ragged), double actor step
     (376, 17, 512, 150, 3, 1, True, 1),     # cfg-3 widths, more rows than 8 resident clusters x 16 -> 32-row tiles
     (33, 5, 512, 300, 3, 2, False, 0),      # 32-row tiles in two waves of clusters, repeat = 2
+    (12, 3, 512, 600, 2, 1, True, 0),       # more rows than one wave of 7 x 80 (forward: 8 clusters of 75 in two waves;
+                                            # BPTT: full waves of 32-row clusters + a remainder launch of 16-row clusters)
 ]
 
 
