@@ -12,6 +12,7 @@
 #include "learner.cuh"
 
 #include <cmath>
+#include <stdlib.h>
 
 #include "elementwise.cuh"
 #include "gemm.cuh"
@@ -69,12 +70,28 @@ int learner_create(Learner** out, const r2d2_learner_config* cfg) {
   l->ws_tc.inference_only = true;
   l->ws_c1.keep_z1_image = true;   // chains whose weights get gradients: the l1 kernel also leaves z1 as the B operand of dW_ih
   l->ws_a1.keep_z1_image = true;
+  {   // R2D2_OVERLAP_INPUTS=0 disables the side stream (A/B)
+    const char* e = getenv("R2D2_OVERLAP_INPUTS");
+    l->overlap_inputs = !(e && e[0] == '0');
+    if (l->overlap_inputs) {
+      int lo = 0, hi = 0;
+      R2D2_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      R2D2_CUDA_TRY(cudaStreamCreateWithPriority(&l->side, cudaStreamNonBlocking, lo));   // lowest priority: leftovers only
+      R2D2_CUDA_TRY(cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming));
+      R2D2_CUDA_TRY(cudaEventCreateWithFlags(&l->ev_c1_inputs, cudaEventDisableTiming));
+      R2D2_CUDA_TRY(cudaEventCreateWithFlags(&l->ev_a1_inputs, cudaEventDisableTiming));
+    }
+  }
   *out = l;
   return R2D2_OK;
 }
 
 int learner_destroy(Learner* l) {
   if (!l) return R2D2_OK;
+  if (l->side) { cudaStreamSynchronize(l->side); cudaStreamDestroy(l->side); }
+  if (l->ev_fork) cudaEventDestroy(l->ev_fork);
+  if (l->ev_c1_inputs) cudaEventDestroy(l->ev_c1_inputs);
+  if (l->ev_a1_inputs) cudaEventDestroy(l->ev_a1_inputs);
   cudaFree(l->arena);
   delete l;
   return R2D2_OK;
@@ -95,7 +112,21 @@ int learner_critic_phase(Learner* l, cudaStream_t st) {
   const float* st_tc = l->states + 6 * BH;   // states[3] = target_critic
 
   // target actor over rows [0, Bn+n+L) from its stored state (learner.py:87,94,106); actions for the last L rows
-  R2D2_TRY(net_forward(l->actor_sh, Pa_t, l->ws_ta, l->obs, nullptr, st_ta, st_ta + BH, Tt, B, 1, st));
+  R2D2_TRY(net_forward_inputs(l->actor_sh, Pa_t, l->ws_ta, l->obs, nullptr, Tt, B, st));
+  if (l->overlap_inputs) {
+    // fork: the input projections of the online critic chain (stored actions) and of the actor's DPG chain need the
+    // batch and weights that nothing in this phase changes.  They are issued on a low-priority side stream right where
+    // the first persistent scan starts: the scans occupy 7 x 16 of the 148 SMs and the projections take the rest.
+    const NetParams Pa = NetParams::from_flat(c.actor_params, l->actor_sh);
+    R2D2_CUDA_TRY(cudaEventRecord(l->ev_fork, st));
+    R2D2_CUDA_TRY(cudaStreamWaitEvent(l->side, l->ev_fork, 0));
+    R2D2_TRY(net_forward_inputs(l->critic_sh, Pc, l->ws_c1, l->obs, l->act, Tc, B, l->side));
+    R2D2_CUDA_TRY(cudaEventRecord(l->ev_c1_inputs, l->side));
+    R2D2_TRY(net_forward_inputs(l->actor_sh, Pa, l->ws_a1, l->obs + (size_t)Bn * B * c.obs_size, nullptr, L, B, l->side));
+    R2D2_CUDA_TRY(cudaEventRecord(l->ev_a1_inputs, l->side));
+    l->a1_inputs_pending = true;
+  }
+  R2D2_TRY(net_forward_scan(l->actor_sh, Pa_t, l->ws_ta, st_ta, st_ta + BH, Tt, B, 1, st));
   R2D2_CUDA_TRY(cudaMemcpyAsync(l->act_tc, l->act, sizeof(float) * (size_t)(Bn + n) * B * A,
                                 cudaMemcpyDeviceToDevice, st));
   R2D2_TRY(net_head_forward(l->actor_sh, Pa_t, l->ws_ta, Bn + n, Tt, B, 1, l->act_tc + (size_t)(Bn + n) * B * A, A, st));
@@ -103,7 +134,9 @@ int learner_critic_phase(Learner* l, cudaStream_t st) {
   R2D2_TRY(net_forward(l->critic_sh, Pc_t, l->ws_tc, l->obs, l->act_tc, st_tc, st_tc + BH, Tt, B, 1, st));
   R2D2_TRY(net_head_forward(l->critic_sh, Pc_t, l->ws_tc, Bn + n, Tt, B, 1, l->q_next, A, st));
   // online critic over rows [0, Bn+L) with stored actions (learner.py:93,105); burn-in stays on the tape (Q4)
-  R2D2_TRY(net_forward(l->critic_sh, Pc, l->ws_c1, l->obs, l->act, st_c, st_c + BH, Tc, B, 1, st));
+  if (l->overlap_inputs) R2D2_CUDA_TRY(cudaStreamWaitEvent(st, l->ev_c1_inputs, 0));
+  else R2D2_TRY(net_forward_inputs(l->critic_sh, Pc, l->ws_c1, l->obs, l->act, Tc, B, st));
+  R2D2_TRY(net_forward_scan(l->critic_sh, Pc, l->ws_c1, st_c, st_c + BH, Tc, B, 1, st));
   R2D2_TRY(net_head_forward(l->critic_sh, Pc, l->ws_c1, Bn, Tc, B, 1, l->q, A, st));
 
   TdPriorityParams tp;
@@ -130,7 +163,13 @@ int learner_actor_forward(Learner* l, cudaStream_t st) {
   const NetParams Pa = NetParams::from_flat(c.actor_params, l->actor_sh);
   const float* obs_l = l->obs + (size_t)Bn * B * O;  // rows [Bn, Bn+L)
   // actor from the zero state, LSTM stepped twice per row (learner.py:117,122-123); mu = output of the 2nd call
-  R2D2_TRY(net_forward(l->actor_sh, Pa, l->ws_a1, obs_l, nullptr, nullptr, nullptr, L, B, 2, st));
+  if (l->a1_inputs_pending) {   // issued on the side stream during the critic phase of this iteration
+    R2D2_CUDA_TRY(cudaStreamWaitEvent(st, l->ev_a1_inputs, 0));
+    l->a1_inputs_pending = false;
+  } else {
+    R2D2_TRY(net_forward_inputs(l->actor_sh, Pa, l->ws_a1, obs_l, nullptr, L, B, st));
+  }
+  R2D2_TRY(net_forward_scan(l->actor_sh, Pa, l->ws_a1, nullptr, nullptr, L, B, 2, st));
   R2D2_TRY(net_head_forward(l->actor_sh, Pa, l->ws_a1, 0, L, B, 2, l->mu, A, st));
   l->actor_forward_done = true;
   l->launches_actor_forward = (int)(launch_count() - launches0);

@@ -10,6 +10,12 @@ struct Learner {
   int rows = 0;            // T' = burn_in + learning + n_step
   int step = 0;            // completed learner iterations (learner.py:82)
   int launches_phase[3] = {0, 0, 0};
+  // side stream for work that depends on the batch and the weights only (the input projections of the online critic
+  // chain and of the actor's DPG chain): it fills the SMs the persistent scans of the target chains leave idle
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_c1_inputs = nullptr, ev_a1_inputs = nullptr;
+  bool overlap_inputs = false;
+  bool a1_inputs_pending = false;    // a1's input projection of this iteration was issued on the side stream
   bool actor_forward_done = false;   // learner_actor_forward already ran for the current iteration
   int launches_actor_forward = 0;
   float* arena = nullptr;

@@ -63,6 +63,14 @@ ChainWs ChainWs::carve(float* base, const NetShape& s, int T, int B, int repeat)
 
 int net_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, const float* obs, const float* act,
                 const float* h0, const float* c0, int T, int B, int repeat, cudaStream_t stream) {
+  R2D2_TRY(net_forward_inputs(s, P, ws, obs, act, T, B, stream));
+  return net_forward_scan(s, P, ws, h0, c0, T, B, repeat, stream);
+}
+
+// The non-recurrent half of a chain: z1 = tanh(l1(x)) and gin = z1 * W_ih^T + b_ih + b_hh for all rows at once.  It
+// depends on the inputs and the weights only, so a caller may run it on another stream long before the scan.
+int net_forward_inputs(const NetShape& s, const NetParams& P, const ChainWs& ws, const float* obs, const float* act,
+                       int T, int B, cudaStream_t stream) {
   const int H = s.hidden, O = s.obs, A = s.act, I = s.in_features();
   const int M = T * B;
   R2D2_REQUIRE(!s.critic || act != nullptr, "critic needs actions");
@@ -95,6 +103,12 @@ int net_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, const 
     if (z1_img) g.A_img = ws.img_k;
     R2D2_TRY(gemm_f32(g, GEMM_NT, stream));
   }
+  return R2D2_OK;
+}
+
+int net_forward_scan(const NetShape& s, const NetParams& P, const ChainWs& ws, const float* h0, const float* c0, int T,
+                     int B, int repeat, cudaStream_t stream) {
+  const int H = s.hidden;
   ScanFwdParams sp;
   sp.gin = ws.gin; sp.whh = P.whh; sp.h0 = h0; sp.c0 = c0;
   sp.gates = ws.gates; sp.hs = ws.hs; sp.cs = ws.cs;

@@ -56,6 +56,11 @@ struct ChainWs {
 // forward over T rows (S = T*repeat steps).  obs [T*B, O], act [T*B, A] (critic).
 int net_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, const float* obs, const float* act,
                 const float* h0, const float* c0, int T, int B, int repeat, cudaStream_t stream);
+// the two halves of net_forward: hoisted input GEMMs (inputs + weights only) and the recurrent scan
+int net_forward_inputs(const NetShape& s, const NetParams& P, const ChainWs& ws, const float* obs, const float* act,
+                       int T, int B, cudaStream_t stream);
+int net_forward_scan(const NetShape& s, const NetParams& P, const ChainWs& ws, const float* h0, const float* c0, int T,
+                     int B, int repeat, cudaStream_t stream);
 // head on rows [first_row, T): out [(T-first_row)*B, A] with leading dimension ldo
 int net_head_forward(const NetShape& s, const NetParams& P, const ChainWs& ws, int first_row, int T, int B,
                      int repeat, float* out, long long ldo, cudaStream_t stream);
