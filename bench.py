@@ -579,6 +579,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    ms_per_rank = [ms]
+    if dist is not None:   # every rank's own device time of the timed loop (they run in lock step through the all-reduces)
+        g = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([ms], device=dev))
+        ms_per_rank = [round(float(x.item()), 4) for x in g]
     ms = max_over_ranks(ms)
     value = world * B * L / (ms * 1e-3)
     log(f"resident arm: {ms:.3f} ms/step; host-fed (e2e) arm")
@@ -644,7 +649,8 @@ def main():
                 "iterations_per_s": world * 1e3 / ms, "rows_per_s": world * B * (cfg.burn_in + L) / (ms * 1e-3),
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clk,
-                "replicas_identical": replicas_identical, "strong_scaling": strong, "other_configs": others}
+                "replicas_identical": replicas_identical, "strong_scaling": strong, "other_configs": others,
+                "ms_per_rank": ms_per_rank, "dp_mode": os.environ.get("R2D2_DP_MODE", "overlap")}
         emit(line)
     arm.close()
     if dist is not None:

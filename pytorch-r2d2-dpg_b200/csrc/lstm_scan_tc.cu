@@ -637,6 +637,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   const int w_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int r8 = w & 7, half = w >> 3;                   // pointwise role: row r8 of row groups e = half, half+2, ...
   const int B = p.B, S = p.T * p.repeat;
+  // H = 512, 32-row tiles: thread = (row tid / 16, the two ADJACENT units 2 (tid % 16), +1) instead of (two rows, one
+  // unit): partial sums, saved activations and operand-tile writes become 8-byte / 4-byte accesses - half the memory
+  // instructions of the cell phase (0.9 of the 3.9 us of a step, tools/trace_bwd.py)
+  constexpr bool PAIR = SM::BIG && NB == 32;
+  auto cell_row = [&](int j) { return PAIR ? (tid >> 4) : 8 * (half + 2 * j) + r8; };
+  auto cell_unit = [&](int j) { return PAIR ? 2 * (tid & 15) + j : lane; };
 
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* dgs = smem + SM::OFF_DG;
@@ -665,7 +671,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   const int ug = rank * 32 + lane;
   const size_t gstride = (size_t)4 * H;
   float dcn[NT], keep[NT][4];
-  float bsum[4] = {0.f, 0.f, 0.f, 0.f};   // this thread's share of the bias gradient: sum of dG over its rows and all steps
+  float bsum[PAIR ? 2 : 1][4];            // this thread's share of the bias gradient: sum of dG over its rows and all steps (per unit)
+#pragma unroll
+  for (int j = 0; j < (PAIR ? 2 : 1); ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bsum[j][q] = 0.f;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     dcn[j] = 0.f;
@@ -738,12 +748,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   const int hrow0 = rel_nx >= 0 ? (rel_nx / p.repeat - (relm_nx == p.repeat - 1 ? 0 : 1)) : 0;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
-    const int b = b0 + 8 * (half + 2 * j) + r8;
+    const int b = b0 + cell_row(j);
+    const int uj = rank * 32 + cell_unit(j);
     rowon[j] = b < b_end;
     const size_t bb = rowon[j] ? (size_t)b : (size_t)b0;
-    gates_nx[j] = p.gates + ((size_t)(S - 1) * B + bb) * gstride + ug;
-    cs_nx[j] = p.cs + ((size_t)(S - 1) * B + bb) * H + ug;
-    head_nx[j] = (p.dh_head && hrow0 >= 0) ? p.dh_head + ((size_t)hrow0 * B + bb) * H + ug : nullptr;
+    gates_nx[j] = p.gates + ((size_t)(S - 1) * B + bb) * gstride + uj;
+    cs_nx[j] = p.cs + ((size_t)(S - 1) * B + bb) * H + uj;
+    head_nx[j] = (p.dh_head && hrow0 >= 0) ? p.dh_head + ((size_t)hrow0 * B + bb) * H + uj : nullptr;
   }
   float pg[NT][4], pc_prev[NT], pc_new[NT], phead[NT];   // saved activations of the step being processed
   auto fetch = [&](float (&g)[NT][4], float (&c)[NT], float (&hd)[NT], bool any) {
@@ -753,12 +764,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       c[j] = hd[j] = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) g[j][q] = 0.f;
-      if (any && rowon[j] && !(p.dbg & 2)) {
+    }
+    if constexpr (PAIR) {   // the two cells are adjacent units of one row: 8-byte loads
+      if (any && rowon[0] && !(p.dbg & 2)) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) g[j][q] = gates_nx[j][q * H];
-        c[j] = __ldg(cs_nx[j]);
-        if (head_now) hd[j] = __ldg(head_nx[j]);
+        for (int q = 0; q < 4; ++q) {
+          const float2 v = *reinterpret_cast<const float2*>(gates_nx[0] + q * H);   // plain load: dgates may alias gates
+          g[0][q] = v.x; g[1][q] = v.y;
+        }
+        const float2 cv = __ldg(reinterpret_cast<const float2*>(cs_nx[0]));
+        c[0] = cv.x; c[1] = cv.y;
+        if (head_now) { const float2 hv = __ldg(reinterpret_cast<const float2*>(head_nx[0])); hd[0] = hv.x; hd[1] = hv.y; }
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        if (any && rowon[j] && !(p.dbg & 2)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) g[j][q] = gates_nx[j][q * H];
+          c[j] = __ldg(cs_nx[j]);
+          if (head_now) hd[j] = __ldg(head_nx[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
       gates_nx[j] -= g_step;
       cs_nx[j] -= h_step;
       if (head_now) head_nx[j] -= h_step;
@@ -791,17 +821,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
     // ---- pointwise backward of the cell (thread = (unit = lane, row r8 of row group e)); the dG values go to the MMA
     // operand tile first - their HBM copies are written below, after the tensor-core step has been started
     float dgr[NT][4];
+    float dhs[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dhs[j] = phead[j];
+    if (it > 0) {
+      if constexpr (PAIR) {
+        if (rowon[0]) {
+          const float* psr = ps + (size_t)cell_row(0) * 32 + cell_unit(0);
+#pragma unroll
+          for (int src = 0; src < C; ++src) {
+            const float2 v = *reinterpret_cast<const float2*>(psr + (size_t)src * NB * 32);
+            dhs[0] += v.x; dhs[1] += v.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int n = cell_row(j);
+          if (rowon[j]) {
+#pragma unroll
+            for (int src = 0; src < C; ++src) dhs[j] += ps[(((SM::BIG ? 0 : buf) * C + src) * NB + n) * 32 + lane];
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      const int n = 8 * (half + 2 * j) + r8, b = b0 + n;
 #pragma unroll
       for (int q = 0; q < 4; ++q) dgr[j][q] = 0.f;
-      if (b < b_end) {
-        float dh = phead[j];
-        if (it > 0) {
-#pragma unroll
-          for (int src = 0; src < C; ++src) dh += ps[(((SM::BIG ? 0 : buf) * C + src) * NB + n) * 32 + lane];
-        }
+      if (rowon[j]) {
+        const float dh = dhs[j];
         const float ig = pg[j][0], fg = pg[j][1], gg = pg[j][2], og = pg[j][3];
         const float tcn = fast_tanh(pc_new[j]);
         const float dc = dcn[j] + dh * og * (1.f - tcn * tcn);
@@ -810,26 +859,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
         dgr[j][1] = dc * pc_prev[j] * fg * (1.f - fg);
         dgr[j][2] = dc * ig * (1.f - gg * gg);
         dcn[j] = dc * fg;
-        // operand tile of the MMA: K index r = q*32 + lane -> chunk (q*4 + lane/8), element lane%8
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __nv_bfloat16 hi, lo;
-          split_bf16(dgr[j][q], hi, lo);
-          const int off = ((q * 4 + (lane >> 3)) * NB + n) * 16 + (lane & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(dgs + off) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(dgs + SM::DG_PLANE + off) = lo;
-          bsum[q] += dgr[j][q];
-        }
+        for (int q = 0; q < 4; ++q) bsum[PAIR ? j : 0][q] += dgr[j][q];
         if (p.repeat > 1) {   // dgin row = sum of dG over the steps that share the input row
 #pragma unroll
           for (int q = 0; q < 4; ++q) keep[j][q] += dgr[j][q];
-          if (emit_gin) {
+        }
+      }
+    }
+    // ---- operand tile of the MMA: K index r = gate*32 + unit -> chunk (gate*4 + unit/8), element unit%8; per-row dgin sums
+    // (repeat > 1) go to their own tile and to HBM when the input row is complete
+    if constexpr (PAIR) {
+      if (rowon[0]) {
+        const int n = cell_row(0), u0 = cell_unit(0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4; ++q) {
+          uint32_t hi, lo;
+          split_pack2(dgr[0][q], dgr[1][q], hi, lo);
+          const int off = ((q * 4 + (u0 >> 3)) * NB + n) * 16 + (u0 & 7) * 2;
+          *reinterpret_cast<uint32_t*>(dgs + off) = hi;
+          *reinterpret_cast<uint32_t*>(dgs + SM::DG_PLANE + off) = lo;
+          if (emit_gin) {
+            if (!p.skip_fp32)
+              *reinterpret_cast<float2*>(p.dgin + ((size_t)t * B + b0 + n) * gstride + q * H + rank * 32 + u0) = make_float2(keep[0][q], keep[1][q]);
+            split_pack2(keep[0][q], keep[1][q], hi, lo);
+            *reinterpret_cast<uint32_t*>(gst + off) = hi;
+            *reinterpret_cast<uint32_t*>(gst + SM::DG_PLANE + off) = lo;
+            keep[0][q] = keep[1][q] = 0.f;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int n = cell_row(j), b = b0 + n;
+        if (rowon[j]) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(dgr[j][q], hi, lo);
+            const int off = ((q * 4 + (lane >> 3)) * NB + n) * 16 + (lane & 7) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(dgs + off) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(dgs + SM::DG_PLANE + off) = lo;
+            if (emit_gin) {
               if (!p.skip_fp32) p.dgin[((size_t)t * B + b) * gstride + q * H + ug] = keep[j][q];
-              __nv_bfloat16 hi, lo;
               split_bf16(keep[j][q], hi, lo);
-              const int off = ((q * 4 + (lane >> 3)) * NB + n) * 16 + (lane & 7) * 2;
               *reinterpret_cast<__nv_bfloat16*>(gst + off) = hi;
               *reinterpret_cast<__nv_bfloat16*>(gst + SM::DG_PLANE + off) = lo;
               keep[j][q] = 0.f;
@@ -842,9 +916,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
       if (!p.skip_fp32) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-          const int b = b0 + 8 * (half + 2 * j) + r8;
-          if (b < b_end) {
-            float* go = p.dgates + ((size_t)s * B + b) * gstride + ug;
+          if (rowon[j]) {
+            float* go = p.dgates + ((size_t)s * B + b0 + cell_row(j)) * gstride + rank * 32 + cell_unit(j);
             go[0] = dgr[j][0]; go[H] = dgr[j][1]; go[2 * H] = dgr[j][2]; go[3 * H] = dgr[j][3];
           }
         }
@@ -1040,15 +1113,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_scan_bwd_tc_kernel(ScanBwd
   tc::fence_before_thread_sync();
   cluster.sync();
   if (p.dbias) {   // CTA-level reduction over the 16 warps (same lane -> unit map), then one atomic per (gate, unit)
-    float* red = ps;       // [warp][4][32] = 8 KB over ps + pstage; all exchange traffic is complete after the cluster barrier
+    float* red = ps;       // [warp | row][4][32] <= 16 KB over ps; all exchange traffic is complete after the cluster barrier
+    constexpr int RED_N = PAIR ? 32 : TC_WARPS;   // partial sums per (gate, unit): one per row (PAIR) or per warp
+    if constexpr (PAIR) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) red[(w * 4 + q) * 32 + lane] = bsum[q];
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[((tid >> 4) * 4 + q) * 32 + cell_unit(j)] = bsum[j][q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red[(w * 4 + q) * 32 + lane] = bsum[0][q];
+    }
     __syncthreads();
     if (tid < 128) {
       const int q = tid >> 5;
       float t = 0.f;
 #pragma unroll
-      for (int ww = 0; ww < TC_WARPS; ++ww) t += red[(ww * 4 + q) * 32 + lane];
+      for (int ww = 0; ww < RED_N; ++ww) t += red[(ww * 4 + q) * 32 + lane];
       atomicAdd(p.dbias + q * H + ug, t);
       if (p.dbias2) atomicAdd(p.dbias2 + q * H + ug, t);
     }

@@ -129,6 +129,10 @@ class LearnerEngine:
         self.world = 1
         self._dist = None
         self._sync = None
+        import os
+        # dev switch for A/B timing: "overlap" (default), "serial" (all-reduces on the compute stream), "none" (no
+        # all-reduce at all: replicas diverge - timing of the lock-step cost only)
+        self._dp_mode = os.environ.get("R2D2_DP_MODE", "overlap")
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -206,15 +210,20 @@ class LearnerEngine:
     def step(self):
         s = nv.current_stream()
         scale = 1.0 / self.world
+        mode = self._dp_mode
         nv.check(self.lib.r2d2_learner_critic_phase(self._h, s))
-        if self._dist is not None:
+        if self._dist is not None and mode == "overlap":
             self._sync.start(self.grads["critic"])                       # side stream
             nv.check(self.lib.r2d2_learner_actor_forward(self._h, s))    # reads no critic weights: overlaps the all-reduce
             self._sync.wait(self.device)
+        elif self._dist is not None and mode == "serial":                # A/B: both all-reduces on the compute stream
+            self._dist.all_reduce(self.grads["critic"])
         nv.check(self.lib.r2d2_learner_actor_phase(self._h, scale, s))
-        if self._dist is not None:
+        if self._dist is not None and mode == "overlap":
             self._sync.start(self.grads["actor"])
             self._sync.wait(self.device)
+        elif self._dist is not None and mode == "serial":
+            self._dist.all_reduce(self.grads["actor"])
         nv.check(self.lib.r2d2_learner_finish_phase(self._h, scale, s))
 
     @property

@@ -22,7 +22,7 @@ for _ in range(2):
     nv.check(lib.r2d2_debug_scan_backward_trace(nv.dptr(gates), nv.dptr(hs), nv.dptr(cs), nv.dptr(whh), nv.dptr(dh), nv.dptr(dgates),
                                                 S, B, H, nv.dptr(trace, torch.int64), st))
 torch.cuda.synchronize()
-for cta in (0, 5, 16 * 3 + 7):
+for cta in (0, 5, 16 * 5 + 7, 16 * 9 + 3, 16 * 13):
     t = trace.cpu().numpy().astype(np.float64)[cta]
     k = slice(20, S - 3)
     d = lambda a, b: float(np.mean(t[k, b] - t[k, a]))
