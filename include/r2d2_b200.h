@@ -250,6 +250,10 @@ int r2d2_learner_actor_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t 
 /* phase 3: actor Adam, step counter, hard target update every target_update_interval steps */
 int r2d2_learner_finish_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t stream);
 int r2d2_learner_step_count(r2d2_learner_t* l);
+/* The critic phase pre-issues the input projection of the actor's DPG chain on a side stream (it reads the actor's
+ * weights).  A caller that runs phase 3 of iteration i AFTER phase 1 of iteration i+1 (deferred actor all-reduce)
+ * switches that off: the weights are not final yet. */
+int r2d2_learner_set_overlap_actor_inputs(r2d2_learner_t* l, int on);
 /* resume: completed iterations so far (drives Adam's bias correction and the target-update period, learner.py:82,131) */
 int r2d2_learner_set_step_count(r2d2_learner_t* l, int step);
 /* number of kernels launched by the three phases of one iteration (bench.py's gpu_launches) */

@@ -237,6 +237,11 @@ int r2d2_learner_finish_phase(r2d2_learner_t* l, float grad_scale, r2d2_stream_t
   return learner_finish_phase(reinterpret_cast<Learner*>(l), grad_scale, S(stream));
 }
 int r2d2_learner_step_count(r2d2_learner_t* l) { return l ? reinterpret_cast<Learner*>(l)->step : -1; }
+int r2d2_learner_set_overlap_actor_inputs(r2d2_learner_t* l, int on) {
+  R2D2_REQUIRE(l, "null");
+  reinterpret_cast<Learner*>(l)->overlap_actor_inputs = on != 0;
+  return R2D2_OK;
+}
 int r2d2_learner_set_step_count(r2d2_learner_t* l, int step) {
   R2D2_REQUIRE(l && step >= 0, "step");
   reinterpret_cast<Learner*>(l)->step = step;

@@ -122,9 +122,11 @@ int learner_critic_phase(Learner* l, cudaStream_t st) {
     R2D2_CUDA_TRY(cudaStreamWaitEvent(l->side, l->ev_fork, 0));
     R2D2_TRY(net_forward_inputs(l->critic_sh, Pc, l->ws_c1, l->obs, l->act, Tc, B, l->side));
     R2D2_CUDA_TRY(cudaEventRecord(l->ev_c1_inputs, l->side));
-    R2D2_TRY(net_forward_inputs(l->actor_sh, Pa, l->ws_a1, l->obs + (size_t)Bn * B * c.obs_size, nullptr, L, B, l->side));
-    R2D2_CUDA_TRY(cudaEventRecord(l->ev_a1_inputs, l->side));
-    l->a1_inputs_pending = true;
+    if (l->overlap_actor_inputs) {   // the actor's weights must be final: not while its optimiser step is still deferred
+      R2D2_TRY(net_forward_inputs(l->actor_sh, Pa, l->ws_a1, l->obs + (size_t)Bn * B * c.obs_size, nullptr, L, B, l->side));
+      R2D2_CUDA_TRY(cudaEventRecord(l->ev_a1_inputs, l->side));
+      l->a1_inputs_pending = true;
+    }
   }
   R2D2_TRY(net_forward_scan(l->actor_sh, Pa_t, l->ws_ta, st_ta, st_ta + BH, Tt, B, 1, st));
   R2D2_CUDA_TRY(cudaMemcpyAsync(l->act_tc, l->act, sizeof(float) * (size_t)(Bn + n) * B * A,

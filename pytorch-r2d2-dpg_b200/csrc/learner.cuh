@@ -15,6 +15,7 @@ struct Learner {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_c1_inputs = nullptr, ev_a1_inputs = nullptr;
   bool overlap_inputs = false;
+  bool overlap_actor_inputs = true;  // off while the caller defers the actor's optimiser step behind the next critic phase
   bool a1_inputs_pending = false;    // a1's input projection of this iteration was issued on the side stream
   bool actor_forward_done = false;   // learner_actor_forward already ran for the current iteration
   int launches_actor_forward = 0;

@@ -110,6 +110,7 @@ class Learner:
         os.replace(tmp, self.model_path + 'model.pt')
 
     def update_target_model(self):
+        self.engine.flush()
         self.engine.flat['target_actor'].copy_(self.engine.flat['actor'])
         self.engine.flat['target_critic'].copy_(self.engine.flat['critic'])
 

@@ -90,6 +90,8 @@ class LearnerEngine:
             raise nv.NativeError("LearnerEngine needs a CUDA device (B200); there is no CPU fallback")
         self.lib = nv.lib()
         self.cfg = cfg
+        self._pending_finish = False          # a deferred phase 3 (data-parallel "defer" mode), see step() / flush()
+        self._h = None
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         torch.cuda.set_device(self.device)
         na = sum(int(np.prod(s)) for s in param_shapes(cfg, False).values())
@@ -132,10 +134,13 @@ class LearnerEngine:
         import os
         # dev switch for A/B timing: "overlap" (default), "serial" (all-reduces on the compute stream), "none" (no
         # all-reduce at all: replicas diverge - timing of the lock-step cost only)
-        self._dp_mode = os.environ.get("R2D2_DP_MODE", "overlap")
+        self._dp_mode = os.environ.get("R2D2_DP_MODE", "defer")
+        self._pending_finish = False
+        self._sync_actor = None
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
+            self._pending_finish = False
             self.lib.r2d2_learner_destroy(self._h)
             self._h = None
 
@@ -147,6 +152,7 @@ class LearnerEngine:
 
     # ---- parameters -------------------------------------------------------------------------
     def views(self, net: str, what: str = "params"):
+        self.flush()
         src = {"params": self.flat, "grads": self.grads, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}[what]
         return flat_views(src[net], self.cfg, "critic" in net)
 
@@ -176,6 +182,9 @@ class LearnerEngine:
             self._dist = dist
             self.world = dist.get_world_size()
             self._sync = GradSync(dist, self.world)
+            self._sync_actor = GradSync(dist, self.world)
+            if self._dp_mode == "defer":   # the actor's weights are final only after the deferred phase 3
+                nv.check(self.lib.r2d2_learner_set_overlap_actor_inputs(self._h, 0))
             for net in ("actor", "critic", "target_actor", "target_critic"):
                 dist.broadcast(self.flat[net], src=0)
             for d in (self.exp_avg, self.exp_avg_sq):
@@ -190,6 +199,7 @@ class LearnerEngine:
         """Data-parallel invariant: parameters and Adam moments are bit-identical on every rank."""
         if self._dist is None:
             return True
+        self.flush()
         ts = [self.flat[n] for n in ("actor", "critic", "target_actor", "target_critic")]
         ts += [d[n] for d in (self.exp_avg, self.exp_avg_sq) for n in ("actor", "critic")]
         return self._sync.replicas_identical(ts)
@@ -208,26 +218,52 @@ class LearnerEngine:
 
     # ---- one learner iteration (learner.py:86-132) on the batch currently in the engine ------------
     def step(self):
+        """One learner iteration.  Data parallel (default mode "defer"): the critic-gradient all-reduce runs on a side
+        stream under the actor's forward chain; the actor-gradient all-reduce is started at the end of the iteration and
+        only WAITED FOR after the next iteration's critic phase (which reads neither the actor nor its gradients) - the
+        actor's Adam step + target update (phase 3) of iteration i run there.  Both synchronisation points are then
+        loose (the ranks may be skewed by milliseconds without waiting for each other): at 8 GPUs the tight version
+        cost 0.6 ms per 12.5 ms step in lock-step jitter although the all-reduce itself takes 75 us
+        (profiles/r02_summary.md).  Iterations whose phase 3 copies the weights into the target nets are not deferred."""
         s = nv.current_stream()
         scale = 1.0 / self.world
-        mode = self._dp_mode
+        mode = self._dp_mode if self._dist is not None else "single"
+        if self._pending_finish and self._finish_updates_targets():
+            self.flush()                                                  # the critic phase below reads the target nets
         nv.check(self.lib.r2d2_learner_critic_phase(self._h, s))
-        if self._dist is not None and mode == "overlap":
+        if mode in ("defer", "overlap"):
             self._sync.start(self.grads["critic"])                       # side stream
+            self.flush()                                                  # phase 3 of the previous iteration (actor Adam)
             nv.check(self.lib.r2d2_learner_actor_forward(self._h, s))    # reads no critic weights: overlaps the all-reduce
             self._sync.wait(self.device)
-        elif self._dist is not None and mode == "serial":                # A/B: both all-reduces on the compute stream
+        elif mode == "serial":                                            # A/B: both all-reduces on the compute stream
             self._dist.all_reduce(self.grads["critic"])
         nv.check(self.lib.r2d2_learner_actor_phase(self._h, scale, s))
-        if self._dist is not None and mode == "overlap":
-            self._sync.start(self.grads["actor"])
-            self._sync.wait(self.device)
-        elif self._dist is not None and mode == "serial":
+        if mode == "defer":
+            self._sync_actor.start(self.grads["actor"])
+            self._pending_finish = True
+            return
+        if mode == "overlap":
+            self._sync_actor.start(self.grads["actor"])
+            self._sync_actor.wait(self.device)
+        elif mode == "serial":
             self._dist.all_reduce(self.grads["actor"])
         nv.check(self.lib.r2d2_learner_finish_phase(self._h, scale, s))
 
+    def _finish_updates_targets(self) -> bool:
+        k = self.cfg.target_interval
+        return k > 0 and (int(self.lib.r2d2_learner_step_count(self._h)) + 1) % k == 0
+
+    def flush(self):
+        """Complete a deferred phase 3 (actor all-reduce wait + Adam + step counter + target update)."""
+        if self._pending_finish:
+            self._sync_actor.wait(self.device)
+            nv.check(self.lib.r2d2_learner_finish_phase(self._h, 1.0 / self.world, nv.current_stream()))
+            self._pending_finish = False
+
     @property
     def step_count(self) -> int:
+        self.flush()
         return int(self.lib.r2d2_learner_step_count(self._h))
 
     # ---- full training state (SURVEY 8f N3: the reference checkpoints weights only and cannot resume) ---------------

@@ -114,6 +114,7 @@ SIGNATURES = {
     "r2d2_learner_finish_phase": (c_int, [c_void_p, c_float, c_void_p]),
     "r2d2_learner_step_count": (c_int, [c_void_p]),
     "r2d2_learner_set_step_count": (c_int, [c_void_p, c_int]),
+    "r2d2_learner_set_overlap_actor_inputs": (c_int, [c_void_p, c_int]),
     "r2d2_learner_launches_per_iteration": (c_int, [c_void_p]),
 }
 
