@@ -650,7 +650,7 @@ def main():
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clk,
                 "replicas_identical": replicas_identical, "strong_scaling": strong, "other_configs": others,
-                "ms_per_rank": ms_per_rank, "dp_mode": os.environ.get("R2D2_DP_MODE", "overlap")}
+                "ms_per_rank": ms_per_rank, "dp_mode": (arm.eng._dp_mode if world > 1 else "single")}
         emit(line)
     arm.close()
     if dist is not None:

@@ -254,6 +254,20 @@ int r2d2_learner_step_count(r2d2_learner_t* l);
  * weights).  A caller that runs phase 3 of iteration i AFTER phase 1 of iteration i+1 (deferred actor all-reduce)
  * switches that off: the weights are not final yet. */
 int r2d2_learner_set_overlap_actor_inputs(r2d2_learner_t* l, int on);
+/* Data-parallel learner, one process per GPU: the two gradient all-reduces of learner.py:113-114,127-128
+ * as kernels of this library over NVLink peer memory, issued inside the phases on the learner's own stream (peer.cuh).
+ * Every rank allocates `bytes` of zeroed device memory that all ranks of the node can map (CUDA IPC / fabric handles;
+ * the Python host side uses torch's symmetric memory), exchanges the addresses and attaches them; the learner's
+ * gradient blocks then live at off_*_grads of its own buffer and the optimiser kernels read off_*_sums.  The caller
+ * keeps calling the phases in the same order on every rank and passes grad_scale = 1 / world.  Call order with the
+ * loosest coupling: critic_phase(i), finish_phase(i-1), actor_forward(i), actor_phase(i). */
+typedef struct {
+  size_t bytes, off_critic_grads, off_actor_grads, off_critic_sums, off_actor_sums;
+} r2d2_peer_layout;
+int r2d2_learner_peer_layout(r2d2_learner_t* l, int world, r2d2_peer_layout* out);
+int r2d2_learner_attach_peers(r2d2_learner_t* l, int rank, int world, void* const* peer_bases);
+/* 0 = fine, 1 = a bounded wait (8 s) for a peer expired: the replicas are no longer in step (synchronises the stream) */
+int r2d2_learner_peer_status(r2d2_learner_t* l, int* status, r2d2_stream_t stream);
 /* resume: completed iterations so far (drives Adam's bias correction and the target-update period, learner.py:82,131) */
 int r2d2_learner_set_step_count(r2d2_learner_t* l, int step);
 /* number of kernels launched by the three phases of one iteration (bench.py's gpu_launches) */

@@ -242,6 +242,26 @@ int r2d2_learner_set_overlap_actor_inputs(r2d2_learner_t* l, int on) {
   reinterpret_cast<Learner*>(l)->overlap_actor_inputs = on != 0;
   return R2D2_OK;
 }
+int r2d2_learner_peer_layout(r2d2_learner_t* lh, int world, r2d2_peer_layout* out) {
+  R2D2_REQUIRE(lh && out && world >= 2 && world <= kPeerMaxWorld, "peer layout arguments");
+  Learner* l = reinterpret_cast<Learner*>(lh);
+  const PeerLayout pl = peer_layout((long long)l->critic_sh.param_count(), (long long)l->actor_sh.param_count(), world);
+  out->bytes = pl.bytes;
+  out->off_critic_grads = pl.off_grads[kPeerCritic];
+  out->off_actor_grads = pl.off_grads[kPeerActor];
+  out->off_critic_sums = pl.off_sums[kPeerCritic];
+  out->off_actor_sums = pl.off_sums[kPeerActor];
+  return R2D2_OK;
+}
+int r2d2_learner_attach_peers(r2d2_learner_t* l, int rank, int world, void* const* peer_bases) {
+  return learner_attach_peers(reinterpret_cast<Learner*>(l), rank, world, peer_bases);
+}
+int r2d2_learner_peer_status(r2d2_learner_t* lh, int* status, r2d2_stream_t stream) {
+  R2D2_REQUIRE(lh && status, "null");
+  Learner* l = reinterpret_cast<Learner*>(lh);
+  R2D2_REQUIRE(l->peer, "no peers attached");
+  return peer_status(*l->peer, status, static_cast<cudaStream_t>(stream));
+}
 int r2d2_learner_set_step_count(r2d2_learner_t* l, int step) {
   R2D2_REQUIRE(l && step >= 0, "step");
   reinterpret_cast<Learner*>(l)->step = step;

@@ -93,6 +93,7 @@ int learner_destroy(Learner* l) {
   if (l->ev_c1_inputs) cudaEventDestroy(l->ev_c1_inputs);
   if (l->ev_a1_inputs) cudaEventDestroy(l->ev_a1_inputs);
   cudaFree(l->arena);
+  delete l->peer;
   delete l;
   return R2D2_OK;
 }
@@ -129,6 +130,9 @@ int learner_critic_phase(Learner* l, cudaStream_t st) {
     }
   }
   R2D2_TRY(net_forward_scan(l->actor_sh, Pa_t, l->ws_ta, st_ta, st_ta + BH, Tt, B, 1, st));
+  // data parallel, deferred actor step: the peers raised "actor gradients complete" at the end of THEIR previous
+  // iteration, one input projection and one scan ago; the sums are needed at the end of this phase
+  if (l->peer) R2D2_TRY(peer_reduce(*l->peer, kPeerActor, st));
   R2D2_CUDA_TRY(cudaMemcpyAsync(l->act_tc, l->act, sizeof(float) * (size_t)(Bn + n) * B * A,
                                 cudaMemcpyDeviceToDevice, st));
   R2D2_TRY(net_head_forward(l->actor_sh, Pa_t, l->ws_ta, Bn + n, Tt, B, 1, l->act_tc + (size_t)(Bn + n) * B * A, A, st));
@@ -151,6 +155,7 @@ int learner_critic_phase(Learner* l, cudaStream_t st) {
 
   R2D2_CUDA_TRY(cudaMemsetAsync(c.critic_grads, 0, sizeof(float) * l->critic_sh.param_count(), st));
   R2D2_TRY(net_backward(l->critic_sh, Pc, &Gc, l->ws_c1, l->obs, l->act, l->dq, Bn, Tc, B, 1, nullptr, nullptr, st));
+  if (l->peer) R2D2_TRY(peer_signal(*l->peer, kPeerCritic, st));
   l->launches_phase[0] = (int)(launch_count() - launches0);
   return R2D2_OK;
 }
@@ -171,6 +176,9 @@ int learner_actor_forward(Learner* l, cudaStream_t st) {
   } else {
     R2D2_TRY(net_forward_inputs(l->actor_sh, Pa, l->ws_a1, obs_l, nullptr, L, B, st));
   }
+  // data parallel: sum this rank's slice of the critic gradients between the input projection and the scan - the
+  // peers signalled one projection ago, the sums are needed one scan later (learner_actor_phase)
+  if (l->peer) R2D2_TRY(peer_reduce(*l->peer, kPeerCritic, st));
   R2D2_TRY(net_forward_scan(l->actor_sh, Pa, l->ws_a1, nullptr, nullptr, L, B, 2, st));
   R2D2_TRY(net_head_forward(l->actor_sh, Pa, l->ws_a1, 0, L, B, 2, l->mu, A, st));
   l->actor_forward_done = true;
@@ -193,7 +201,8 @@ int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t st) {
   l->actor_forward_done = false;
   const long long launches1 = launch_count();
   (void)launches1;
-  R2D2_TRY(adam_step(c.critic_params, c.critic_grads, c.critic_exp_avg, c.critic_exp_avg_sq,
+  if (l->peer) R2D2_TRY(peer_wait(*l->peer, kPeerCritic, st));
+  R2D2_TRY(adam_step(c.critic_params, l->optimiser_grads(kPeerCritic), c.critic_exp_avg, c.critic_exp_avg_sq,
                      (long long)l->critic_sh.param_count(), l->step + 1, c.critic_lr, 0.9f, 0.999f, 1e-8f,
                      grad_scale, st));                                                     // learner.py:114
 
@@ -208,6 +217,7 @@ int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t st) {
                         l->mu, st));
   R2D2_CUDA_TRY(cudaMemsetAsync(c.actor_grads, 0, sizeof(float) * l->actor_sh.param_count(), st));
   R2D2_TRY(net_backward(l->actor_sh, Pa, &Ga, l->ws_a1, obs_l, nullptr, l->dpre_actor, 0, L, B, 2, nullptr, nullptr, st));
+  if (l->peer) R2D2_TRY(peer_signal(*l->peer, kPeerActor, st));
   l->launches_phase[1] = (int)(launch_count() - launches0) + extra;
   return R2D2_OK;
 }
@@ -215,7 +225,8 @@ int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t st) {
 int learner_finish_phase(Learner* l, float grad_scale, cudaStream_t st) {
   const r2d2_learner_config& c = l->cfg;
   const long long launches0 = launch_count();
-  R2D2_TRY(adam_step(c.actor_params, c.actor_grads, c.actor_exp_avg, c.actor_exp_avg_sq,
+  if (l->peer) R2D2_TRY(peer_wait(*l->peer, kPeerActor, st));   // runs the slice reduction first if no critic phase did
+  R2D2_TRY(adam_step(c.actor_params, l->optimiser_grads(kPeerActor), c.actor_exp_avg, c.actor_exp_avg_sq,
                      (long long)l->actor_sh.param_count(), l->step + 1, c.actor_lr, 0.9f, 0.999f, 1e-8f, grad_scale,
                      st));                                                                 // learner.py:128
   l->step += 1;
@@ -226,6 +237,24 @@ int learner_finish_phase(Learner* l, float grad_scale, cudaStream_t st) {
                                   cudaMemcpyDeviceToDevice, st));
   }
   l->launches_phase[2] = (int)(launch_count() - launches0);
+  return R2D2_OK;
+}
+
+int learner_attach_peers(Learner* l, int rank, int world, void* const* peer_bases) {
+  R2D2_REQUIRE(l && peer_bases, "null argument");
+  R2D2_REQUIRE(world >= 2 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "peer rank / world");
+  R2D2_REQUIRE(!l->peer, "peers already attached");
+  PeerExchange* x = new PeerExchange();
+  x->rank = rank;
+  x->world = world;
+  x->lay = peer_layout((long long)l->critic_sh.param_count(), (long long)l->actor_sh.param_count(), world);
+  for (int k = 0; k < world; ++k) {
+    if (!peer_bases[k]) { delete x; R2D2_REQUIRE(false, "null peer buffer"); }
+    x->ptrs.base[k] = static_cast<char*>(peer_bases[k]);
+  }
+  l->peer = x;
+  l->cfg.critic_grads = x->grads(kPeerCritic);
+  l->cfg.actor_grads = x->grads(kPeerActor);
   return R2D2_OK;
 }
 

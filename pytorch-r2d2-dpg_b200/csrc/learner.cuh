@@ -1,6 +1,7 @@
 #pragma once
 #include "common.cuh"
 #include "net.cuh"
+#include "peer.cuh"
 
 namespace r2d2 {
 
@@ -29,6 +30,12 @@ struct Learner {
         *q_pi = nullptr, *dq_pi = nullptr, *dpre_actor = nullptr, *td_sq = nullptr, *priority = nullptr,
         *losses = nullptr;
   ChainWs ws_ta, ws_tc, ws_c1, ws_a1, ws_c2;
+  // data-parallel learner: gradient blocks live in a peer-mapped buffer and are summed by peer.cu's kernels in this
+  // learner's own stream (null: single GPU, or the caller reduces cfg.*_grads itself between the phases)
+  PeerExchange* peer = nullptr;
+  const float* optimiser_grads(int block) const {
+    return peer ? peer->sums(block) : (block == kPeerCritic ? cfg.critic_grads : cfg.actor_grads);
+  }
 };
 
 int learner_create(Learner** out, const r2d2_learner_config* cfg);
@@ -37,5 +44,8 @@ int learner_critic_phase(Learner* l, cudaStream_t stream);
 int learner_actor_forward(Learner* l, cudaStream_t stream);
 int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t stream);
 int learner_finish_phase(Learner* l, float grad_scale, cudaStream_t stream);
+// peer_bases[k] = rank k's exchange buffer (peer_layout(...).bytes, zeroed, mapped into this process); moves the
+// learner's gradient blocks into peer_bases[rank]
+int learner_attach_peers(Learner* l, int rank, int world, void* const* peer_bases);
 
 }  // namespace r2d2

@@ -11,7 +11,7 @@ replay_memory.py:67-136) with the sum tree in HBM.
 from __future__ import annotations
 
 from collections import OrderedDict
-from ctypes import byref, c_longlong, c_void_p
+from ctypes import byref, c_int, c_longlong, c_void_p
 from dataclasses import dataclass
 
 import numpy as np
@@ -132,17 +132,30 @@ class LearnerEngine:
         self._dist = None
         self._sync = None
         import os
-        # dev switch for A/B timing: "overlap" (default), "serial" (all-reduces on the compute stream), "none" (no
-        # all-reduce at all: replicas diverge - timing of the lock-step cost only)
-        self._dp_mode = os.environ.get("R2D2_DP_MODE", "defer")
+        # data-parallel gradient exchange: "peer" (default: the library's own kernels over NVLink peer memory, in the
+        # learner's stream), "defer" (NCCL all-reduces on a side stream, the actor's waited for one critic phase later;
+        # also the fallback when no peer-mapped buffer can be set up), A/B timing only: "overlap" (NCCL, both waited for
+        # where needed), "serial" (NCCL on the compute stream), "none" (no exchange at all: replicas diverge)
+        self._dp_mode = os.environ.get("R2D2_DP_MODE", "peer")
+        self._peer_buf = None
+        self._peer_hdl = None
         self._pending_finish = False
         self._sync_actor = None
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
+            if getattr(self, "_peer_buf", None) is not None:
+                # peers read this rank's gradient block until their last slice sum ran: completing the pending phase 3
+                # (its wait kernel needs every peer's "slice delivered" flag) proves nobody touches the buffer any more
+                try:
+                    self.flush()
+                    torch.cuda.synchronize(self.device)
+                except Exception:
+                    pass
             self._pending_finish = False
             self.lib.r2d2_learner_destroy(self._h)
             self._h = None
+            self._peer_buf = self._peer_hdl = None
 
     def __del__(self):
         try:
@@ -183,7 +196,9 @@ class LearnerEngine:
             self.world = dist.get_world_size()
             self._sync = GradSync(dist, self.world)
             self._sync_actor = GradSync(dist, self.world)
-            if self._dp_mode == "defer":   # the actor's weights are final only after the deferred phase 3
+            if self._dp_mode == "peer":
+                self._attach_peers(dist)
+            if self._dp_mode in ("peer", "defer"):   # the actor's weights are final only after the deferred phase 3
                 nv.check(self.lib.r2d2_learner_set_overlap_actor_inputs(self._h, 0))
             for net in ("actor", "critic", "target_actor", "target_critic"):
                 dist.broadcast(self.flat[net], src=0)
@@ -195,11 +210,55 @@ class LearnerEngine:
                                  "r2d2_b200.dist_env.DistEnv.from_environ().init_process_group() first "
                                  "(the drop-in learner.Learner does)")
 
+    def _attach_peers(self, dist):
+        """Move the gradient blocks into a buffer every rank of the node maps (torch symmetric memory: CUDA fabric /
+        IPC handles exchanged through the process group's store) and hand the peer addresses to the library.  All ranks
+        agree on the outcome; if any rank cannot map its peers, every rank falls back to the NCCL "defer" mode."""
+        ok, why = 1, ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            lay = nv.PeerLayout()
+            nv.check(self.lib.r2d2_learner_peer_layout(self._h, self.world, byref(lay)))
+            buf = symm.empty(int(lay.bytes) // 4, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, dist.group.WORLD.group_name)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or int(hdl.rank) != dist.get_rank() or ptrs[dist.get_rank()] != buf.data_ptr():
+                raise RuntimeError("symmetric-memory handle does not match the process group")
+        except Exception as e:  # noqa: BLE001 - any failure means "no peer mapping on this box"
+            ok, why = 0, repr(e)[:200]
+        agreed = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        if int(agreed.item()) == 0:
+            if dist.get_rank() == 0:
+                print(f"[r2d2_b200] no peer-mapped gradient buffer ({why or 'another rank failed'}): "
+                      "gradient exchange falls back to NCCL all-reduces (R2D2_DP_MODE=defer)", flush=True)
+            self._dp_mode = "defer"
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier()                                   # every rank's flag words are zero before anyone signals
+        arr = (c_void_p * self.world)(*ptrs)
+        nv.check(self.lib.r2d2_learner_attach_peers(self._h, dist.get_rank(), self.world, arr))
+        self._peer_buf, self._peer_hdl = buf, hdl
+        na, nc = self.grads["actor"].numel(), self.grads["critic"].numel()
+        oc, oa = int(lay.off_critic_grads) // 4, int(lay.off_actor_grads) // 4
+        self.grads = {"actor": buf[oa:oa + na], "critic": buf[oc:oc + nc]}
+
+    def peer_status(self) -> int:
+        """0, or 1 when a bounded wait for a peer's flag expired inside the gradient-exchange kernels."""
+        if self._peer_buf is None:
+            return 0
+        st = c_int(0)
+        nv.check(self.lib.r2d2_learner_peer_status(self._h, byref(st), nv.current_stream()))
+        return int(st.value)
+
     def replicas_identical(self) -> bool:
         """Data-parallel invariant: parameters and Adam moments are bit-identical on every rank."""
         if self._dist is None:
             return True
         self.flush()
+        if self.peer_status() != 0:
+            return False
         ts = [self.flat[n] for n in ("actor", "critic", "target_actor", "target_critic")]
         ts += [d[n] for d in (self.exp_avg, self.exp_avg_sq) for n in ("actor", "critic")]
         return self._sync.replicas_identical(ts)
@@ -231,6 +290,12 @@ class LearnerEngine:
         if self._pending_finish and self._finish_updates_targets():
             self.flush()                                                  # the critic phase below reads the target nets
         nv.check(self.lib.r2d2_learner_critic_phase(self._h, s))
+        if mode == "peer":   # signal / slice-sum / wait kernels are issued by the phases themselves (csrc/peer.cuh)
+            self.flush()                                                  # phase 3 of the previous iteration
+            nv.check(self.lib.r2d2_learner_actor_forward(self._h, s))
+            nv.check(self.lib.r2d2_learner_actor_phase(self._h, scale, s))
+            self._pending_finish = True
+            return
         if mode in ("defer", "overlap"):
             self._sync.start(self.grads["critic"])                       # side stream
             self.flush()                                                  # phase 3 of the previous iteration (actor Adam)
@@ -257,7 +322,8 @@ class LearnerEngine:
     def flush(self):
         """Complete a deferred phase 3 (actor all-reduce wait + Adam + step counter + target update)."""
         if self._pending_finish:
-            self._sync_actor.wait(self.device)
+            if self._dp_mode != "peer":
+                self._sync_actor.wait(self.device)
             nv.check(self.lib.r2d2_learner_finish_phase(self._h, 1.0 / self.world, nv.current_stream()))
             self._pending_finish = False
 

@@ -51,6 +51,11 @@ class LearnerConfig(Structure):
                 ("critic_exp_avg_sq", c_void_p)]
 
 
+class PeerLayout(Structure):
+    _fields_ = [(k, c_size_t) for k in ("bytes", "off_critic_grads", "off_actor_grads", "off_critic_sums",
+                                        "off_actor_sums")]
+
+
 class LearnerBuffers(Structure):
     _fields_ = [(k, c_void_p) for k in ("obs", "act", "rew", "term", "states", "leaf_idx", "uniforms",
                                         "q_value", "target_q_value", "td_sq", "priority", "losses")]
@@ -115,6 +120,9 @@ SIGNATURES = {
     "r2d2_learner_step_count": (c_int, [c_void_p]),
     "r2d2_learner_set_step_count": (c_int, [c_void_p, c_int]),
     "r2d2_learner_set_overlap_actor_inputs": (c_int, [c_void_p, c_int]),
+    "r2d2_learner_peer_layout": (c_int, [c_void_p, c_int, POINTER(PeerLayout)]),
+    "r2d2_learner_attach_peers": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "r2d2_learner_peer_status": (c_int, [c_void_p, POINTER(c_int), c_void_p]),
     "r2d2_learner_launches_per_iteration": (c_int, [c_void_p]),
 }
 

@@ -13,10 +13,10 @@ from oracle import ref_port
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode):
     import torch.distributed as dist
     from r2d2_b200 import engine
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), R2D2_DP_MODE=mode)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     B = 16
@@ -24,21 +24,23 @@ def _worker(rank, world, port, out_dir):
     cfg = engine.PathConfig(obs=6, act=2, hidden=64, batch=B // world, burn_in=4, learning=6, n_step=2)
     eng = engine.LearnerEngine(cfg, device=f"cuda:{rank}", seed=5)
     eng.enable_data_parallel()
+    assert eng._dp_mode == mode, f"gradient exchange fell back to {eng._dp_mode}"
     init = {n: {k: v.cpu().numpy().copy() for k, v in eng.views(n).items()} for n in ("actor", "critic")}
     sh = B // world
-    for it in range(2):
+    for it in range(3):
         full = ref_port.synthetic_batch(pc, seed=10 + it)
         shard = {k: np.ascontiguousarray(v[:, rank * sh:(rank + 1) * sh]) for k, v in full.items()}
         eng.set_batch(shard)
         eng.step()
     torch.cuda.synchronize()
+    assert eng.replicas_identical() and eng.peer_status() == 0
     np.savez(os.path.join(out_dir, f"dp_rank{rank}.npz"), **{f"{n}/{k}": v.cpu().numpy() for n in ("actor", "critic")
                                                             for k, v in eng.views(n).items()})
     if rank == 0:
         cfg1 = engine.PathConfig(obs=6, act=2, hidden=64, batch=B, burn_in=4, learning=6, n_step=2)
         single = engine.LearnerEngine(cfg1, device="cuda:0", seed=5)
         single.load_state_dicts(init["actor"], init["critic"])
-        for it in range(2):
+        for it in range(3):
             single.set_batch(ref_port.synthetic_batch(pc, seed=10 + it))
             single.step()
         torch.cuda.synchronize()
@@ -49,12 +51,15 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_data_parallel_matches_single_gpu():
+@pytest.mark.parametrize("mode", ["peer", "defer"])
+def test_two_gpu_data_parallel_matches_single_gpu(mode):
+    """mode "peer": the library's own signal / slice-sum / wait kernels over NVLink peer memory (csrc/peer.cu, the
+    default); "defer": NCCL all-reduces on a side stream (the fallback)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(2, 29600 + os.getpid() % 200, d), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, 29600 + os.getpid() % 200 + (7 if mode == "peer" else 0), d, mode), nprocs=2, join=True)
         r0, r1, one = (np.load(os.path.join(d, f)) for f in ("dp_rank0.npz", "dp_rank1.npz", "single.npz"))
         for k in r0.files:
             assert np.array_equal(r0[k], r1[k]), f"replicas diverged: {k}"
