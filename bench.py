@@ -270,12 +270,18 @@ class Arm:
         self.rp = build_replay(engine_mod, self.cfg, episodes, self.ep_len, seed=seed_base + rank, device=dev)
         self.gen = torch.Generator(device=dev).manual_seed(1234 + rank)
 
+    def _next_batch(self, eng, used):
+        """LearnerEngine.step's prefetch hook: tree write-back of the batch just used (learner.py:136-139), then the
+        sum-tree draw + gather of the next one (learner.py:84) - the same work per iteration as the sequential loop,
+        issued as soon as the priorities exist so that the next batch's target chains can run mid-iteration."""
+        self.rp.update_priorities(used.leaf_idx, used.priority)
+        self.rp.sample_into(eng, generator=self.gen)
+
     def step_resident(self):
-        self.rp.sample_into(self.eng, generator=self.gen)
-        self.eng.step()
-        self.rp.update_priorities(self.eng.leaf_idx, self.eng.priority)
+        self.eng.step(prefetch=self._next_batch)
 
     def time_resident(self, steps, warmup, barrier, clocks=None):
+        self.rp.sample_into(self.eng, generator=self.gen)     # batch 0; every step draws its successor
         for _ in range(warmup):
             self.step_resident()
         barrier()
@@ -326,22 +332,30 @@ class Arm:
                     stage[s_][k].copy_(v, non_blocking=True)
                 ready[s_].record(copy_stream)
 
-        def step_host(i):
+        def fill(i):         # batch i: device sampler, then the host-built batch of the same shape over it
             s_ = i % 2
             cur = torch.cuda.current_stream()
             rp.sample_into(eng, generator=self.gen)               # sum-tree draw + gather (device sampler, learner.py:84)
             cur.wait_event(ready[s_])
-            for k in keys:                                        # the host-built batch of this step (H2D done on the copy stream)
+            for k in keys:                                        # H2D ran on the copy stream; this is the on-device hand-over
                 getattr(eng, k).copy_(stage[s_][k], non_blocking=True)
             consumed[s_].record(cur)
             prefetch(i + 1)
-            eng.step()
-            rp.update_priorities(eng.leaf_idx, eng.priority)      # learner.py:136-139
+
+        def step_host(i):
+            cur = torch.cuda.current_stream()
+
+            def next_batch(eng_, used):
+                rp.update_priorities(used.leaf_idx, used.priority)    # learner.py:136-139
+                fill(i + 1)
+
+            eng.step(prefetch=next_batch)
             host_prio.copy_(eng.priority, non_blocking=True)
             host_loss.copy_(eng.losses, non_blocking=True)
             cur.synchronize()                                     # the host consumes the priorities every iteration
 
         prefetch(0)
+        fill(0)
         for i in range(warmup):
             step_host(i)
         barrier()

@@ -238,7 +238,16 @@ typedef struct {
 int r2d2_learner_create(r2d2_learner_t** out, const r2d2_learner_config* cfg);
 int r2d2_learner_destroy(r2d2_learner_t* l);
 int r2d2_learner_buffers_get(r2d2_learner_t* l, r2d2_learner_buffers* out);
-/* phase 1: target chains, online critic chain, TD/priority kernel, critic BPTT -> critic_grads */
+/* The batch has two slots.  r2d2_learner_buffers_get returns slot 0 (the only one a simple caller needs); a pipelined
+ * caller fills slot 1-s with batch i+1 while the phases of iteration i still read slot s, runs that batch's target
+ * chains early with r2d2_learner_target_phase (they read only the target nets: learner.py:87,94-95,106) and switches
+ * with r2d2_learner_select_batch before the next r2d2_learner_critic_phase.  Not allowed between an iteration whose
+ * finish phase copies the weights into the target nets and that finish phase (the targets would be stale). */
+int r2d2_learner_buffers_get_slot(r2d2_learner_t* l, int slot, r2d2_learner_buffers* out);
+int r2d2_learner_select_batch(r2d2_learner_t* l, int slot);
+int r2d2_learner_target_phase(r2d2_learner_t* l, int slot, r2d2_stream_t stream);
+/* phase 1: target chains (unless r2d2_learner_target_phase already ran for the selected slot), online critic chain,
+ * TD/priority kernel, critic BPTT -> critic_grads */
 int r2d2_learner_critic_phase(r2d2_learner_t* l, r2d2_stream_t stream);
 /* optional, between phase 1 and phase 2: the actor's forward chain of the DPG update (learner.py:117,120-123; zero
  * state, 2 cell steps per row).  It does not read the critic, so a data-parallel caller issues it while the

@@ -220,6 +220,23 @@ int r2d2_learner_buffers_get(r2d2_learner_t* lh, r2d2_learner_buffers* o) {
   o->td_sq = l->td_sq; o->priority = l->priority; o->losses = l->losses;
   return R2D2_OK;
 }
+int r2d2_learner_buffers_get_slot(r2d2_learner_t* lh, int slot, r2d2_learner_buffers* o) {
+  R2D2_REQUIRE(lh && o && (slot == 0 || slot == 1), "batch slot");
+  Learner* l = reinterpret_cast<Learner*>(lh);
+  R2D2_TRY(r2d2_learner_buffers_get(lh, o));
+  const Learner::BatchSlot& b = l->slots[slot];
+  o->obs = b.obs; o->act = b.act; o->rew = b.rew; o->term = b.term; o->states = b.states;
+  o->leaf_idx = b.leaf_idx; o->uniforms = b.uniforms;
+  return R2D2_OK;
+}
+int r2d2_learner_select_batch(r2d2_learner_t* l, int slot) {
+  R2D2_REQUIRE(l, "null");
+  return learner_select_batch(reinterpret_cast<Learner*>(l), slot);
+}
+int r2d2_learner_target_phase(r2d2_learner_t* l, int slot, r2d2_stream_t stream) {
+  R2D2_REQUIRE(l, "null");
+  return learner_target_phase(reinterpret_cast<Learner*>(l), slot, S(stream));
+}
 int r2d2_learner_critic_phase(r2d2_learner_t* l, r2d2_stream_t stream) {
   R2D2_REQUIRE(l, "null");
   return learner_critic_phase(reinterpret_cast<Learner*>(l), S(stream));
@@ -270,7 +287,8 @@ int r2d2_learner_set_step_count(r2d2_learner_t* l, int step) {
 int r2d2_learner_launches_per_iteration(r2d2_learner_t* lh) {
   if (!lh) return -1;
   Learner* l = reinterpret_cast<Learner*>(lh);
-  return l->launches_phase[0] + l->launches_phase[1] + l->launches_phase[2];
+  return l->launches_phase[0] + l->launches_phase[1] + l->launches_phase[2] +
+         (l->target_phase_standalone ? l->launches_target : 0);
 }
 
 }  // extern "C"

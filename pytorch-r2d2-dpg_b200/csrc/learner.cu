@@ -43,7 +43,7 @@ int learner_create(Learner** out, const r2d2_learner_config* cfg) {
   const size_t n_obs = align64((size_t)Tw * B * O), n_act = align64((size_t)Tw * B * A), n_rt = align64((size_t)Tw * B);
   const size_t n_states = align64((size_t)8 * B * H), n_lba = align64((size_t)L * B * A);
   const size_t n_acttc = align64((size_t)Tt * B * A);
-  total += n_obs + n_act + 2 * n_rt + n_states + align64(B) /*uniforms*/ + align64(2 * (size_t)B) /*leaf idx (int64)*/;
+  total += 2 * (n_obs + n_act + 2 * n_rt + n_states + align64(B) /*uniforms*/ + align64(2 * (size_t)B) /*leaf idx (int64)*/);
   total += n_acttc + 8 * n_lba + align64((size_t)L * B) + align64(B) + 64;
   const size_t ws_ta = ChainWs::floats(l->actor_sh, Tt, B, 1), ws_tc = ChainWs::floats(l->critic_sh, Tt, B, 1);
   const size_t ws_c1 = ChainWs::floats(l->critic_sh, Tc, B, 1), ws_a1 = ChainWs::floats(l->actor_sh, L, B, 2);
@@ -54,9 +54,12 @@ int learner_create(Learner** out, const r2d2_learner_config* cfg) {
   l->arena_floats = total;
   float* p = l->arena;
   auto take = [&](size_t nfl) { float* r = p; p += align64(nfl); return r; };
-  l->obs = take(n_obs); l->act = take(n_act); l->rew = take(n_rt); l->term = take(n_rt);
-  l->states = take(n_states); l->uniforms = take(B);
-  l->leaf_idx = reinterpret_cast<long long*>(take(2 * (size_t)B));
+  for (auto& b : l->slots) {
+    b.obs = take(n_obs); b.act = take(n_act); b.rew = take(n_rt); b.term = take(n_rt);
+    b.states = take(n_states); b.uniforms = take(B);
+    b.leaf_idx = reinterpret_cast<long long*>(take(2 * (size_t)B));
+  }
+  learner_select_batch(l, 0);
   l->act_tc = take(n_acttc);
   l->q = take(n_lba); l->q_next = take(n_lba); l->target = take(n_lba); l->dq = take(n_lba);
   l->mu = take(n_lba); l->q_pi = take(n_lba); l->dq_pi = take(n_lba); l->dpre_actor = take(n_lba);
@@ -98,52 +101,98 @@ int learner_destroy(Learner* l) {
   return R2D2_OK;
 }
 
-int learner_critic_phase(Learner* l, cudaStream_t st) {
+int learner_select_batch(Learner* l, int slot) {
+  R2D2_REQUIRE(l && (slot == 0 || slot == 1), "batch slot");
+  const Learner::BatchSlot& b = l->slots[slot];
+  l->cur_slot = slot;
+  l->obs = b.obs; l->act = b.act; l->rew = b.rew; l->term = b.term; l->states = b.states; l->uniforms = b.uniforms;
+  l->leaf_idx = b.leaf_idx;
+  return R2D2_OK;
+}
+
+int learner_target_phase(Learner* l, int slot, cudaStream_t st) {
+  R2D2_REQUIRE(l && (slot == 0 || slot == 1), "batch slot");
   const r2d2_learner_config& c = l->cfg;
   const int B = c.batch, Bn = c.burn_in, L = c.learning, n = c.n_step, A = c.n_actions, H = c.hidden;
   const int Tt = Bn + n + L, Tc = Bn + L;
   const long long launches0 = launch_count();
+  const Learner::BatchSlot& b = l->slots[slot];
+  const bool ahead = slot != l->cur_slot;   // batch i+1 while the phases of iteration i are still running on the other slot
   const NetParams Pa_t = NetParams::from_flat(c.target_actor_params, l->actor_sh);
   const NetParams Pc_t = NetParams::from_flat(c.target_critic_params, l->critic_sh);
-  const NetParams Pc = NetParams::from_flat(c.critic_params, l->critic_sh);
-  const NetParams Gc = NetParams::from_flat(c.critic_grads, l->critic_sh);
   const size_t BH = (size_t)B * H;
-  const float* st_ta = l->states + 2 * BH;   // states[1] = target_actor (hx, cx)
-  const float* st_c = l->states + 4 * BH;    // states[2] = critic
-  const float* st_tc = l->states + 6 * BH;   // states[3] = target_critic
+  const float* st_ta = b.states + 2 * BH;   // states[1] = target_actor (hx, cx)
+  const float* st_tc = b.states + 6 * BH;   // states[3] = target_critic
 
   // target actor over rows [0, Bn+n+L) from its stored state (learner.py:87,94,106); actions for the last L rows
-  R2D2_TRY(net_forward_inputs(l->actor_sh, Pa_t, l->ws_ta, l->obs, nullptr, Tt, B, st));
+  R2D2_TRY(net_forward_inputs(l->actor_sh, Pa_t, l->ws_ta, b.obs, nullptr, Tt, B, st));
   if (l->overlap_inputs) {
-    // fork: the input projections of the online critic chain (stored actions) and of the actor's DPG chain need the
-    // batch and weights that nothing in this phase changes.  They are issued on a low-priority side stream right where
-    // the first persistent scan starts: the scans occupy 7 x 16 of the 148 SMs and the projections take the rest.
-    const NetParams Pa = NetParams::from_flat(c.actor_params, l->actor_sh);
-    R2D2_CUDA_TRY(cudaEventRecord(l->ev_fork, st));
-    R2D2_CUDA_TRY(cudaStreamWaitEvent(l->side, l->ev_fork, 0));
-    R2D2_TRY(net_forward_inputs(l->critic_sh, Pc, l->ws_c1, l->obs, l->act, Tc, B, l->side));
-    R2D2_CUDA_TRY(cudaEventRecord(l->ev_c1_inputs, l->side));
-    if (l->overlap_actor_inputs) {   // the actor's weights must be final: not while its optimiser step is still deferred
+    // fork: input projections that need the batch and weights nothing in this phase changes are issued on a
+    // low-priority side stream right where the first persistent scan starts: the scans occupy 7 x 16 of the 148 SMs
+    // and the projections take the rest.  Same slot: the online critic chain of this batch (stored actions).  The
+    // actor's DPG chain of the iteration in flight: when its weights are final - always when running ahead (the caller
+    // completes the previous optimiser step first), else unless the caller defers that step (overlap_actor_inputs).
+    bool forked = false;
+    auto fork = [&]() -> int {
+      if (!forked) {
+        R2D2_CUDA_TRY(cudaEventRecord(l->ev_fork, st));
+        R2D2_CUDA_TRY(cudaStreamWaitEvent(l->side, l->ev_fork, 0));
+        forked = true;
+      }
+      return R2D2_OK;
+    };
+    if (!ahead && l->c1_inputs_slot != slot) {
+      const NetParams Pc = NetParams::from_flat(c.critic_params, l->critic_sh);
+      R2D2_TRY(fork());
+      R2D2_TRY(net_forward_inputs(l->critic_sh, Pc, l->ws_c1, b.obs, b.act, Tc, B, l->side));
+      R2D2_CUDA_TRY(cudaEventRecord(l->ev_c1_inputs, l->side));
+      l->c1_inputs_slot = slot;
+    }
+    if ((ahead || l->overlap_actor_inputs) && !l->a1_inputs_pending && !l->actor_forward_done) {
+      const NetParams Pa = NetParams::from_flat(c.actor_params, l->actor_sh);
+      R2D2_TRY(fork());
       R2D2_TRY(net_forward_inputs(l->actor_sh, Pa, l->ws_a1, l->obs + (size_t)Bn * B * c.obs_size, nullptr, L, B, l->side));
       R2D2_CUDA_TRY(cudaEventRecord(l->ev_a1_inputs, l->side));
       l->a1_inputs_pending = true;
     }
   }
   R2D2_TRY(net_forward_scan(l->actor_sh, Pa_t, l->ws_ta, st_ta, st_ta + BH, Tt, B, 1, st));
-  // data parallel, deferred actor step: the peers raised "actor gradients complete" at the end of THEIR previous
-  // iteration, one input projection and one scan ago; the sums are needed at the end of this phase
-  if (l->peer) R2D2_TRY(peer_reduce(*l->peer, kPeerActor, st));
-  R2D2_CUDA_TRY(cudaMemcpyAsync(l->act_tc, l->act, sizeof(float) * (size_t)(Bn + n) * B * A,
-                                cudaMemcpyDeviceToDevice, st));
+  // data parallel: this rank's slice sums of whichever gradient block was signalled last - the peers signalled one
+  // input projection and one scan ago (peer.cuh); both calls are no-ops without a pending signal
+  if (l->peer) {
+    R2D2_TRY(peer_reduce(*l->peer, kPeerCritic, st));
+    R2D2_TRY(peer_reduce(*l->peer, kPeerActor, st));
+  }
+  R2D2_CUDA_TRY(cudaMemcpyAsync(l->act_tc, b.act, sizeof(float) * (size_t)(Bn + n) * B * A, cudaMemcpyDeviceToDevice, st));
   R2D2_TRY(net_head_forward(l->actor_sh, Pa_t, l->ws_ta, Bn + n, Tt, B, 1, l->act_tc + (size_t)(Bn + n) * B * A, A, st));
   // target critic: stored actions while burning in, target-actor actions afterwards (learner.py:95,106)
-  R2D2_TRY(net_forward(l->critic_sh, Pc_t, l->ws_tc, l->obs, l->act_tc, st_tc, st_tc + BH, Tt, B, 1, st));
+  R2D2_TRY(net_forward(l->critic_sh, Pc_t, l->ws_tc, b.obs, l->act_tc, st_tc, st_tc + BH, Tt, B, 1, st));
   R2D2_TRY(net_head_forward(l->critic_sh, Pc_t, l->ws_tc, Bn + n, Tt, B, 1, l->q_next, A, st));
+  l->targets_slot = slot;
+  l->launches_target = (int)(launch_count() - launches0);
+  return R2D2_OK;
+}
+
+int learner_critic_phase(Learner* l, cudaStream_t st) {
+  const r2d2_learner_config& c = l->cfg;
+  const int B = c.batch, Bn = c.burn_in, L = c.learning, n = c.n_step, A = c.n_actions, H = c.hidden;
+  const int Tc = Bn + L;
+  const long long launches0 = launch_count();
+  const NetParams Pc = NetParams::from_flat(c.critic_params, l->critic_sh);
+  const NetParams Gc = NetParams::from_flat(c.critic_grads, l->critic_sh);
+  const size_t BH = (size_t)B * H;
+  const float* st_c = l->states + 4 * BH;    // states[2] = critic
+
+  l->target_phase_standalone = l->targets_slot == l->cur_slot;
+  if (!l->target_phase_standalone) R2D2_TRY(learner_target_phase(l, l->cur_slot, st));
   // online critic over rows [0, Bn+L) with stored actions (learner.py:93,105); burn-in stays on the tape (Q4)
-  if (l->overlap_inputs) R2D2_CUDA_TRY(cudaStreamWaitEvent(st, l->ev_c1_inputs, 0));
+  if (l->c1_inputs_slot == l->cur_slot) R2D2_CUDA_TRY(cudaStreamWaitEvent(st, l->ev_c1_inputs, 0));
   else R2D2_TRY(net_forward_inputs(l->critic_sh, Pc, l->ws_c1, l->obs, l->act, Tc, B, st));
+  l->c1_inputs_slot = -1;
   R2D2_TRY(net_forward_scan(l->critic_sh, Pc, l->ws_c1, st_c, st_c + BH, Tc, B, 1, st));
+  if (l->peer) R2D2_TRY(peer_reduce(*l->peer, kPeerActor, st));   // no target phase in this call: first scan is this one
   R2D2_TRY(net_head_forward(l->critic_sh, Pc, l->ws_c1, Bn, Tc, B, 1, l->q, A, st));
+  l->targets_slot = -1;   // q_next is consumed by the TD kernel below
 
   TdPriorityParams tp;
   tp.q = l->q; tp.q_next = l->q_next; tp.rew = l->rew; tp.term = l->term;
@@ -205,6 +254,19 @@ int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t st) {
   R2D2_TRY(adam_step(c.critic_params, l->optimiser_grads(kPeerCritic), c.critic_exp_avg, c.critic_exp_avg_sq,
                      (long long)l->critic_sh.param_count(), l->step + 1, c.critic_lr, 0.9f, 0.999f, 1e-8f,
                      grad_scale, st));                                                     // learner.py:114
+  {
+    // the other slot already holds the next batch (its target chains ran ahead): the input projection of ITS online
+    // critic chain needs the weights Adam just wrote and nothing else - side stream, under the scans of this phase
+    const int other = 1 - l->cur_slot;
+    if (l->overlap_inputs && l->targets_slot == other && l->c1_inputs_slot != other) {
+      const Learner::BatchSlot& nb = l->slots[other];
+      R2D2_CUDA_TRY(cudaEventRecord(l->ev_fork, st));
+      R2D2_CUDA_TRY(cudaStreamWaitEvent(l->side, l->ev_fork, 0));
+      R2D2_TRY(net_forward_inputs(l->critic_sh, Pc, l->ws_c1, nb.obs, nb.act, Bn + L, B, l->side));
+      R2D2_CUDA_TRY(cudaEventRecord(l->ev_c1_inputs, l->side));
+      l->c1_inputs_slot = other;
+    }
+  }
 
   const float* obs_l = l->obs + (size_t)Bn * B * O;  // rows [Bn, Bn+L)
   // critic (post-Adam weights, zero state) on the actor's actions; loss = mean(-Q) (learner.py:118,123-124)

@@ -22,7 +22,19 @@ struct Learner {
   int launches_actor_forward = 0;
   float* arena = nullptr;
   size_t arena_floats = 0;
-  // batch (filled by replay_sample or by the caller)
+  // batch (filled by replay_sample or by the caller).  Two slots: while the phases of iteration i still read slot s, the
+  // caller may fill slot 1-s with batch i+1 and run its target chains early (learner_target_phase) - they read the
+  // target nets only, so they are the independent work between "critic gradients complete" and "sums needed" of the
+  // data-parallel gradient exchange.  obs .. leaf_idx below always point into slots[cur_slot].
+  struct BatchSlot {
+    float *obs = nullptr, *act = nullptr, *rew = nullptr, *term = nullptr, *states = nullptr, *uniforms = nullptr;
+    long long* leaf_idx = nullptr;
+  } slots[2];
+  int cur_slot = 0;
+  int targets_slot = -1;        // slot whose target-chain outputs (q_next) are current; -1: none
+  int c1_inputs_slot = -1;      // slot whose online-critic input projection is in flight / done on the side stream
+  int launches_target = 0;      // launches of the last learner_target_phase
+  bool target_phase_standalone = false;
   float *obs = nullptr, *act = nullptr, *rew = nullptr, *term = nullptr, *states = nullptr, *uniforms = nullptr;
   long long* leaf_idx = nullptr;
   // intermediates / results
@@ -40,6 +52,10 @@ struct Learner {
 
 int learner_create(Learner** out, const r2d2_learner_config* cfg);
 int learner_destroy(Learner* l);
+int learner_select_batch(Learner* l, int slot);
+// target chains of the batch in `slot` (learner.py:87,94-95,106): q_next for the next learner_critic_phase on that slot.
+// Reads the target nets and the batch only.  learner_critic_phase runs it itself when the current slot has none.
+int learner_target_phase(Learner* l, int slot, cudaStream_t stream);
 int learner_critic_phase(Learner* l, cudaStream_t stream);
 int learner_actor_forward(Learner* l, cudaStream_t stream);
 int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t stream);

@@ -127,13 +127,28 @@ class Learner:
                 print('learner memory sequence size:', self.memory.sequence_counter)
         step = 0
         dev = self.memory._dev
+
+        def next_batch(eng, used):
+            # priorities of the batch just trained on (learner.py:135-139), then the next draw (learner.py:84): the
+            # engine calls this as soon as the priorities exist and runs the next batch's target chains mid-iteration
+            dev.update_priorities(used.leaf_idx, used.priority)
+            dev.sample_into(eng)
+
+        have_batch = False
         while max_steps is None or step < max_steps:
             if step % 100 == 0 and self.dist_env.is_main:
                 print('learning step:', step)
             step += 1
-            dev.sample_into(self.engine)                               # learner.py:84
-            self.engine.step()                                         # learner.py:86-132
-            dev.update_priorities(self.engine.leaf_idx, self.engine.priority)   # learner.py:135-139
+            if not have_batch:
+                dev.sample_into(self.engine)                           # learner.py:84
+            if step % self.memory_update_interval == 0 or step == max_steps:
+                # an ingest follows this step: it may evict rows, so no batch is drawn ahead of it
+                self.engine.step()                                     # learner.py:86-132
+                dev.update_priorities(self.engine.leaf_idx, self.engine.priority)   # learner.py:135-139
+                have_batch = False
+            else:
+                self.engine.step(prefetch=next_batch)
+                have_batch = True
             if step % self.model_save_interval == 0:
                 self.save_model()
                 if os.environ.get("R2D2_SAVE_STATE", "1") == "1":

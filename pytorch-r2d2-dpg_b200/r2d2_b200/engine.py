@@ -112,17 +112,21 @@ class LearnerEngine:
                              self.exp_avg["critic"].data_ptr(), self.exp_avg_sq["critic"].data_ptr())
         self._h = c_void_p()
         nv.check(self.lib.r2d2_learner_create(byref(self._h), byref(c)))
-        b = nv.LearnerBuffers()
-        nv.check(self.lib.r2d2_learner_buffers_get(self._h, byref(b)))
         T, B, O, A, H, L = cfg.rows, cfg.batch, cfg.obs, cfg.act, cfg.hidden, cfg.learning
         dev = self.device
-        self.obs = nv.view_f32(b.obs, (T, B, O), dev)
-        self.act = nv.view_f32(b.act, (T, B, A), dev)
-        self.rew = nv.view_f32(b.rew, (T, B), dev)
-        self.term = nv.view_f32(b.term, (T, B), dev)
-        self.states = nv.view_f32(b.states, (4, 2, B, H), dev)
-        self.leaf_idx = nv.view_i64(b.leaf_idx, (B,), dev)
-        self.uniforms = nv.view_f32(b.uniforms, (B,), dev)
+        # the batch has two slots (include/r2d2_b200.h): the attributes obs .. uniforms are views of the slot the NEXT
+        # sample goes to; a plain caller never leaves slot 0
+        self._slots = []
+        for slot in (0, 1):
+            b = nv.LearnerBuffers()
+            nv.check(self.lib.r2d2_learner_buffers_get_slot(self._h, slot, byref(b)))
+            self._slots.append({"obs": nv.view_f32(b.obs, (T, B, O), dev), "act": nv.view_f32(b.act, (T, B, A), dev),
+                                "rew": nv.view_f32(b.rew, (T, B), dev), "term": nv.view_f32(b.term, (T, B), dev),
+                                "states": nv.view_f32(b.states, (4, 2, B, H), dev),
+                                "leaf_idx": nv.view_i64(b.leaf_idx, (B,), dev),
+                                "uniforms": nv.view_f32(b.uniforms, (B,), dev)})
+        self._lib_slot = 0
+        self._bind_slot(0)
         self.q_value = nv.view_f32(b.q_value, (L * B, A), dev)
         self.target_q_value = nv.view_f32(b.target_q_value, (L * B, A), dev)
         self.td_sq = nv.view_f32(b.td_sq, (L * B,), dev)
@@ -141,6 +145,11 @@ class LearnerEngine:
         self._peer_hdl = None
         self._pending_finish = False
         self._sync_actor = None
+
+    def _bind_slot(self, slot: int):
+        for k, v in self._slots[slot].items():
+            setattr(self, k, v)
+        self._fill_slot = slot
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -276,25 +285,45 @@ class LearnerEngine:
             self.states[i].copy_(cv(batch[k]))
 
     # ---- one learner iteration (learner.py:86-132) on the batch currently in the engine ------------
-    def step(self):
-        """One learner iteration.  Data parallel (default mode "defer"): the critic-gradient all-reduce runs on a side
-        stream under the actor's forward chain; the actor-gradient all-reduce is started at the end of the iteration and
-        only WAITED FOR after the next iteration's critic phase (which reads neither the actor nor its gradients) - the
-        actor's Adam step + target update (phase 3) of iteration i run there.  Both synchronisation points are then
-        loose (the ranks may be skewed by milliseconds without waiting for each other): at 8 GPUs the tight version
-        cost 0.6 ms per 12.5 ms step in lock-step jitter although the all-reduce itself takes 75 us
-        (profiles/r02_summary.md).  Iterations whose phase 3 copies the weights into the target nets are not deferred."""
+    def step(self, prefetch=None):
+        """One learner iteration on the batch in the engine (learner.py:86-132).
+
+        `prefetch(engine, used)`, if given, is called exactly once per step and must (1) write back the priorities of
+        the batch this step trained on - `used.leaf_idx`, `used.priority` - and (2) fill the engine's batch buffers
+        (`obs .. states`, e.g. `DeviceReplay.sample_into`) with the NEXT batch.  It is called as early as the data flow
+        allows - right after the critic phase, when the priorities exist - and the next batch's target chains run
+        straight away, in the middle of this iteration: they read only the target nets, so they are the independent
+        work that lets the data-parallel ranks drift by a millisecond or two without waiting for each other (and on
+        one GPU the input projections hide under their scans as before).  On iterations whose finish phase copies
+        into the target nets it is called at the end of the step instead.
+
+        Data parallel, mode "peer" (default): the gradient blocks are summed by the library's own kernels over NVLink
+        peer memory inside the phases (csrc/peer.cuh); the actor's optimiser step of iteration i runs after the critic
+        phase of iteration i+1.  Mode "defer": the same schedule with NCCL all-reduces on a side stream."""
         s = nv.current_stream()
         scale = 1.0 / self.world
         mode = self._dp_mode if self._dist is not None else "single"
+        if self._fill_slot != self._lib_slot:
+            nv.check(self.lib.r2d2_learner_select_batch(self._h, self._fill_slot))
+            self._lib_slot = self._fill_slot
         if self._pending_finish and self._finish_updates_targets():
-            self.flush()                                                  # the critic phase below reads the target nets
+            self.flush()                                                  # the target chains below read the target nets
         nv.check(self.lib.r2d2_learner_critic_phase(self._h, s))
-        if mode == "peer":   # signal / slice-sum / wait kernels are issued by the phases themselves (csrc/peer.cuh)
-            self.flush()                                                  # phase 3 of the previous iteration
+        if mode in ("peer", "single", "none"):
+            if mode == "peer":
+                self.flush()                                              # phase 3 of the previous iteration
+            ahead = prefetch is not None and not self._finish_updates_targets()
+            if ahead:
+                self._run_prefetch(prefetch)
+                nv.check(self.lib.r2d2_learner_target_phase(self._h, self._fill_slot, s))
             nv.check(self.lib.r2d2_learner_actor_forward(self._h, s))
             nv.check(self.lib.r2d2_learner_actor_phase(self._h, scale, s))
-            self._pending_finish = True
+            if mode == "peer":   # signal / slice-sum / wait kernels are issued by the phases themselves
+                self._pending_finish = True
+            else:
+                nv.check(self.lib.r2d2_learner_finish_phase(self._h, scale, s))
+            if prefetch is not None and not ahead:
+                self._run_prefetch(prefetch)
             return
         if mode in ("defer", "overlap"):
             self._sync.start(self.grads["critic"])                       # side stream
@@ -307,13 +336,21 @@ class LearnerEngine:
         if mode == "defer":
             self._sync_actor.start(self.grads["actor"])
             self._pending_finish = True
-            return
-        if mode == "overlap":
-            self._sync_actor.start(self.grads["actor"])
-            self._sync_actor.wait(self.device)
-        elif mode == "serial":
-            self._dist.all_reduce(self.grads["actor"])
-        nv.check(self.lib.r2d2_learner_finish_phase(self._h, scale, s))
+        else:
+            if mode == "overlap":
+                self._sync_actor.start(self.grads["actor"])
+                self._sync_actor.wait(self.device)
+            elif mode == "serial":
+                self._dist.all_reduce(self.grads["actor"])
+            nv.check(self.lib.r2d2_learner_finish_phase(self._h, scale, s))
+        if prefetch is not None:
+            self._run_prefetch(prefetch)
+
+    def _run_prefetch(self, prefetch):
+        from types import SimpleNamespace
+        used = SimpleNamespace(leaf_idx=self.leaf_idx, priority=self.priority, losses=self.losses)
+        self._bind_slot(1 - self._fill_slot)     # the phases still in flight keep reading the other slot
+        prefetch(self, used)
 
     def _finish_updates_targets(self) -> bool:
         k = self.cfg.target_interval

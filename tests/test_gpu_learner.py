@@ -249,3 +249,39 @@ def test_training_state_resume_continues_the_run(eng_mod):
         assert rel_l2(a.exp_avg[net].cpu().numpy(), b.exp_avg[net].cpu().numpy()) < 1e-4
         assert rel_l2(a.exp_avg_sq[net].cpu().numpy(), b.exp_avg_sq[net].cpu().numpy()) < 1e-4
     assert torch.equal(a.flat["target_critic"], a.flat["critic"]) == torch.equal(b.flat["target_critic"], b.flat["critic"])
+
+
+@pytest.mark.parametrize("hidden,batch", [(64, 8), (128, 32)])
+def test_pipelined_step_matches_sequential(eng_mod, hidden, batch):
+    """`step(prefetch=...)`: the next batch is drawn mid-iteration into the second batch slot and its target chains run
+    before the actor phase of the iteration in flight (r2d2_learner_target_phase); on iterations that copy into the
+    target nets the hook is called at the end instead.  Same batches in the same order must give the same run as the
+    sequential sample -> step -> write-back loop, including the priorities handed to the hook."""
+    kw = dict(obs=6, act=2, hidden=hidden, batch=batch, burn_in=4, learning=6, n_step=2, target_interval=3)
+    pc = ref_port.PathConfig(**kw)
+    cfg = eng_mod.PathConfig(**kw)
+    steps = 8                                               # crosses two hard target updates
+    batches = [ref_port.synthetic_batch(pc, seed=40 + it) for it in range(steps + 1)]
+    seq = eng_mod.LearnerEngine(cfg, seed=3)
+    seq_prio = []
+    for it in range(steps):
+        seq.set_batch(batches[it])
+        seq.step()
+        seq_prio.append(seq.priority.clone())
+    pip = eng_mod.LearnerEngine(cfg, seed=3)
+    pip_prio, calls = [], []
+    pip.set_batch(batches[0])
+    for it in range(steps):
+        def hook(eng, used, it=it):
+            calls.append(it)
+            pip_prio.append(used.priority.clone())
+            eng.set_batch(batches[it + 1])
+        pip.step(prefetch=hook)
+    torch.cuda.synchronize()
+    assert calls == list(range(steps))
+    assert pip.step_count == seq.step_count == steps
+    for it in range(steps):
+        assert rel_l2(pip_prio[it].cpu().numpy(), seq_prio[it].cpu().numpy()) < 1e-5, it
+    for net in ("actor", "critic", "target_actor", "target_critic"):
+        assert rel_l2(pip.flat[net].cpu().numpy(), seq.flat[net].cpu().numpy()) < 1e-5, net
+    assert pip.launches_per_iteration == seq.launches_per_iteration
