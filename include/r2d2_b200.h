@@ -275,8 +275,11 @@ typedef struct {
 } r2d2_peer_layout;
 int r2d2_learner_peer_layout(r2d2_learner_t* l, int world, r2d2_peer_layout* out);
 int r2d2_learner_attach_peers(r2d2_learner_t* l, int rank, int world, void* const* peer_bases);
-/* 0 = fine, 1 = a bounded wait (8 s) for a peer expired: the replicas are no longer in step (synchronises the stream) */
+/* 0 = fine, 1 = a bounded wait (4 s) for a peer expired: the replicas are no longer in step (synchronises the stream) */
 int r2d2_learner_peer_status(r2d2_learner_t* l, int* status, r2d2_stream_t stream);
+/* diagnostics: nanoseconds summed since the last reset - [0..1] the slice-sum kernel waited for the peers' "gradients
+ * complete" (critic, actor block), [2..3] the slice-sum kernel ran in total, [4..5] the wait kernel waited */
+int r2d2_learner_peer_counters(r2d2_learner_t* l, unsigned long long* out6, int reset, r2d2_stream_t stream);
 /* resume: completed iterations so far (drives Adam's bias correction and the target-update period, learner.py:82,131) */
 int r2d2_learner_set_step_count(r2d2_learner_t* l, int step);
 /* number of kernels launched by the three phases of one iteration (bench.py's gpu_launches) */

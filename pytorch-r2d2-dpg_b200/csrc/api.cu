@@ -279,6 +279,12 @@ int r2d2_learner_peer_status(r2d2_learner_t* lh, int* status, r2d2_stream_t stre
   R2D2_REQUIRE(l->peer, "no peers attached");
   return peer_status(*l->peer, status, static_cast<cudaStream_t>(stream));
 }
+int r2d2_learner_peer_counters(r2d2_learner_t* lh, unsigned long long* out6, int reset, r2d2_stream_t stream) {
+  R2D2_REQUIRE(lh && out6, "null");
+  Learner* l = reinterpret_cast<Learner*>(lh);
+  R2D2_REQUIRE(l->peer, "no peers attached");
+  return peer_counters(*l->peer, out6, reset, static_cast<cudaStream_t>(stream));
+}
 int r2d2_learner_set_step_count(r2d2_learner_t* l, int step) {
   R2D2_REQUIRE(l && step >= 0, "step");
   reinterpret_cast<Learner*>(l)->step = step;

@@ -1,6 +1,8 @@
 // Gradient exchange over NVLink peer memory - see peer.cuh.
 #include "peer.cuh"
 
+#include <stdlib.h>
+
 namespace r2d2 {
 
 namespace {
@@ -10,7 +12,10 @@ constexpr int kFlagIn = 0;        // [2][16]  written by peer k at [block][k]: "
 constexpr int kFlagOut = 32;      // [2][16]  written by peer k at [block][k]: "my slice of iteration e is in your sums"
 constexpr int kFlagCounter = 64;  // [2]      CTAs of the local reduce kernel that finished
 constexpr int kFlagStatus = 66;   // [1]      1 = a bounded wait expired
-constexpr unsigned long long kSpinLimitNs = 8000000000ull;
+// diagnostics (u64, byte offset 512): [0..1] ns the slice-sum kernel of block b waited for the peers' "gradients
+// complete", [2..3] ns it ran in total, [4..5] ns the wait kernel of block b waited for "slice delivered", [6] start stamp
+constexpr size_t kCounterBytes = 512;
+constexpr unsigned long long kSpinLimitNs = 4000000000ull;
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   unsigned v;
@@ -33,6 +38,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // epochs only grow; a peer is at most one ahead
 __device__ __forceinline__ void spin_until(const unsigned* flag, unsigned value, unsigned* status) {
   const unsigned long long t0 = global_ns();
+  if (*reinterpret_cast<volatile unsigned*>(status)) return;   // a wait already expired: the run is lost, do not stall it further
   while ((int)(ld_acquire_sys(flag) - value) < 0) {
     if (global_ns() - t0 > kSpinLimitNs) {
       *status = 1u;
@@ -50,16 +56,26 @@ __global__ void peer_signal_kernel(PeerPtrs p, int world, int rank, size_t off_w
   }
 }
 
-__global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned value, unsigned* status) {
+__global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned value, unsigned* status,
+                                 unsigned long long* waited_ns) {
+  const unsigned long long t0 = global_ns();
   if ((int)threadIdx.x < world) spin_until(flags + threadIdx.x, value, status);
+  __syncthreads();
+  if (threadIdx.x == 0) *waited_ns += global_ns() - t0;
 }
 
 __global__ void __launch_bounds__(512)
 peer_reduce_kernel(PeerPtrs p, int world, int rank, size_t off_flags, int block, size_t off_grads, size_t off_sums,
                    long long slice_vec, unsigned value) {
   unsigned* flags = reinterpret_cast<unsigned*>(p.base[rank] + off_flags);
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(p.base[rank] + off_flags + kCounterBytes);
+  const unsigned long long t0 = global_ns();
   if ((int)threadIdx.x < world) spin_until(flags + kFlagIn + block * kPeerMaxWorld + threadIdx.x, value, flags + kFlagStatus);
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counters[block] += global_ns() - t0;
+    counters[6] = t0;
+  }
   const long long first = (long long)rank * slice_vec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slice_vec; i += (long long)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -81,6 +97,7 @@ peer_reduce_kernel(PeerPtrs p, int world, int rank, size_t off_flags, int block,
     const unsigned done = atomicAdd(counter, 1u) + 1u;
     if (done == gridDim.x) {   // last CTA: every slice store of this rank is ordered before the flags
       *counter = 0u;
+      counters[2 + block] += global_ns() - counters[6];
       __threadfence_system();
       for (int k = 0; k < world; ++k)
         st_release_sys(reinterpret_cast<unsigned*>(p.base[k] + off_flags) + kFlagOut + block * kPeerMaxWorld + rank, value);
@@ -89,6 +106,12 @@ peer_reduce_kernel(PeerPtrs p, int world, int rank, size_t off_flags, int block,
 }
 
 }  // namespace
+
+// R2D2_PEER_DRY=1 (timing A/B only): buffers attached, no exchange kernels - the optimiser reads zeros
+static bool peer_dry() {
+  const char* e = getenv("R2D2_PEER_DRY");
+  return e && e[0] == '1';
+}
 
 PeerLayout peer_layout(long long n_critic, long long n_actor, int world) {
   PeerLayout l;
@@ -107,6 +130,7 @@ int peer_signal(PeerExchange& x, int block, cudaStream_t stream) {
   R2D2_REQUIRE(block == 0 || block == 1, "peer block");
   R2D2_REQUIRE(!x.reduce_pending[block] && !x.wait_pending[block], "peer_signal: the previous exchange of this block is not complete");
   x.epoch[block] += 1;
+  if (peer_dry()) return R2D2_OK;
   peer_signal_kernel<<<1, 32, 0, stream>>>(x.ptrs, x.world, x.rank,
                                            x.lay.off_flags + sizeof(unsigned) * (kFlagIn + block * kPeerMaxWorld), x.epoch[block]);
   count_launch();
@@ -133,7 +157,8 @@ int peer_wait(PeerExchange& x, int block, cudaStream_t stream) {
   R2D2_TRY(peer_reduce(x, block, stream));
   if (!x.wait_pending[block]) return R2D2_OK;
   unsigned* flags = reinterpret_cast<unsigned*>(x.ptrs.base[x.rank] + x.lay.off_flags);
-  peer_wait_kernel<<<1, 32, 0, stream>>>(flags + kFlagOut + block * kPeerMaxWorld, x.world, x.epoch[block], flags + kFlagStatus);
+  peer_wait_kernel<<<1, 32, 0, stream>>>(flags + kFlagOut + block * kPeerMaxWorld, x.world, x.epoch[block], flags + kFlagStatus,
+                                         reinterpret_cast<unsigned long long*>(x.ptrs.base[x.rank] + x.lay.off_flags + kCounterBytes) + 4 + block);
   count_launch();
   R2D2_CUDA_TRY(cudaGetLastError());
   x.wait_pending[block] = false;
@@ -146,6 +171,14 @@ int peer_status(const PeerExchange& x, int* out, cudaStream_t stream) {
                                 cudaMemcpyDeviceToHost, stream));
   R2D2_CUDA_TRY(cudaStreamSynchronize(stream));
   *out = (int)v;
+  return R2D2_OK;
+}
+
+int peer_counters(const PeerExchange& x, unsigned long long* out6, int reset, cudaStream_t stream) {
+  char* c = x.ptrs.base[x.rank] + x.lay.off_flags + kCounterBytes;
+  R2D2_CUDA_TRY(cudaMemcpyAsync(out6, c, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  if (reset) R2D2_CUDA_TRY(cudaMemsetAsync(c, 0, 6 * sizeof(unsigned long long), stream));
+  R2D2_CUDA_TRY(cudaStreamSynchronize(stream));
   return R2D2_OK;
 }
 

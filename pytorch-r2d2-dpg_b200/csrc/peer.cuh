@@ -41,5 +41,8 @@ int peer_reduce(PeerExchange& x, int block, cudaStream_t stream);   // no-op unl
 int peer_wait(PeerExchange& x, int block, cudaStream_t stream);     // runs a pending reduce first
 // 0 = fine; 1 = a bounded wait for a peer's flag expired (the results of that iteration are garbage)
 int peer_status(const PeerExchange& x, int* out, cudaStream_t stream);
+// diagnostics, ns summed since the last reset: [0..1] slice-sum kernel waiting for the peers' signal (critic, actor),
+// [2..3] slice-sum kernel in total, [4..5] wait kernel
+int peer_counters(const PeerExchange& x, unsigned long long* out6, int reset, cudaStream_t stream);
 
 }  // namespace r2d2

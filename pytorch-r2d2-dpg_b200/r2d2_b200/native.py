@@ -125,6 +125,7 @@ SIGNATURES = {
     "r2d2_learner_target_phase": (c_int, [c_void_p, c_int, c_void_p]),
     "r2d2_learner_peer_layout": (c_int, [c_void_p, c_int, POINTER(PeerLayout)]),
     "r2d2_learner_attach_peers": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "r2d2_learner_peer_counters": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "r2d2_learner_peer_status": (c_int, [c_void_p, POINTER(c_int), c_void_p]),
     "r2d2_learner_launches_per_iteration": (c_int, [c_void_p]),
 }

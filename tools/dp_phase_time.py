@@ -23,6 +23,7 @@ NAMES = ["critic_phase", "flush(prev actor step)", "tree update + sample", "targ
 
 def run(variant):
     os.environ["R2D2_DP_MODE"] = variant.split("_")[0]
+    os.environ["R2D2_PEER_DRY"] = "1" if variant.endswith("_dry") else "0"
     arm = bench.Arm(engine, bench.CONFIGS["cfg3"], dev, env.rank, 96, data_parallel=dist is not None)
     eng, lib = arm.eng, arm.eng.lib
     mode = eng._dp_mode if dist is not None else "none"
@@ -68,6 +69,10 @@ def run(variant):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    import ctypes
+    cnt = (ctypes.c_ulonglong * 6)()
+    if eng._peer_buf is not None:
+        nv.check(lib.r2d2_learner_peer_counters(eng._h, cnt, 1, nv.current_stream()))
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for i in range(STEPS):
@@ -76,7 +81,11 @@ def run(variant):
     torch.cuda.synchronize()
     seg = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / STEPS for i in range(len(NAMES))]
     total = t0.elapsed_time(t1) / STEPS
-    row = torch.tensor(seg + [total], device=dev)
+    extra = [0.0] * 6
+    if eng._peer_buf is not None:
+        nv.check(lib.r2d2_learner_peer_counters(eng._h, cnt, 0, nv.current_stream()))
+        extra = [cnt[i] * 1e-6 / STEPS for i in range(6)]
+    row = torch.tensor(seg + [total] + extra, device=dev)
     rows = [torch.zeros_like(row) for _ in range(env.world)]
     if dist is not None:
         dist.all_gather(rows, row)
@@ -84,7 +93,9 @@ def run(variant):
         rows = [row]
     if env.rank == 0:
         print(f"== {variant} (mode {mode}) ms per iteration, one column per rank")
-        for i, n in enumerate(NAMES + ["TOTAL"]):
+        for i, n in enumerate(NAMES + ["TOTAL", "slice sum (critic): waiting", "slice sum (actor): waiting",
+                               "slice sum (critic): total", "slice sum (actor): total", "wait kernel (critic)",
+                               "wait kernel (actor)"]):
             print(f"  {n:26s} " + " ".join(f"{r[i].item():8.3f}" for r in rows))
         sys.stdout.flush()
     arm.close()
