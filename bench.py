@@ -659,7 +659,9 @@ def main():
                         "d2h_bytes_per_step": d2h,
                         "feed": "per step: sum-tree draw + gather on the device, the step's batch copied from PINNED HOST memory "
                                 "(copy stream, overlaps the previous step) over the gathered one, learner iteration, tree "
-                                "write-back, priorities + losses read back to the host and the stream synchronised"},
+                                "write-back, priorities + losses read back to the host and the stream synchronised "
+                                "(write-back of batch i and draw + host copy of batch i+1 are issued as soon as the "
+                                "priorities of batch i exist: LearnerEngine.step(prefetch=...))"},
                 "iterations_per_s": world * 1e3 / ms, "rows_per_s": world * B * (cfg.burn_in + L) / (ms * 1e-3),
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clk,
