@@ -274,6 +274,8 @@ typedef struct {
   size_t bytes, off_critic_grads, off_actor_grads, off_critic_sums, off_actor_sums;
 } r2d2_peer_layout;
 int r2d2_learner_peer_layout(r2d2_learner_t* l, int world, r2d2_peer_layout* out);
+/* the same from the two parameter counts (host arithmetic only) */
+int r2d2_peer_layout_for(long long n_critic, long long n_actor, int world, r2d2_peer_layout* out);
 int r2d2_learner_attach_peers(r2d2_learner_t* l, int rank, int world, void* const* peer_bases);
 /* 0 = fine, 1 = a bounded wait (4 s) for a peer expired: the replicas are no longer in step (synchronises the stream) */
 int r2d2_learner_peer_status(r2d2_learner_t* l, int* status, r2d2_stream_t stream);

@@ -259,6 +259,16 @@ int r2d2_learner_set_overlap_actor_inputs(r2d2_learner_t* l, int on) {
   reinterpret_cast<Learner*>(l)->overlap_actor_inputs = on != 0;
   return R2D2_OK;
 }
+int r2d2_peer_layout_for(long long n_critic, long long n_actor, int world, r2d2_peer_layout* out) {
+  R2D2_REQUIRE(out && n_critic > 0 && n_actor > 0 && world >= 2 && world <= kPeerMaxWorld, "peer layout arguments");
+  const PeerLayout pl = peer_layout(n_critic, n_actor, world);
+  out->bytes = pl.bytes;
+  out->off_critic_grads = pl.off_grads[kPeerCritic];
+  out->off_actor_grads = pl.off_grads[kPeerActor];
+  out->off_critic_sums = pl.off_sums[kPeerCritic];
+  out->off_actor_sums = pl.off_sums[kPeerActor];
+  return R2D2_OK;
+}
 int r2d2_learner_peer_layout(r2d2_learner_t* lh, int world, r2d2_peer_layout* out) {
   R2D2_REQUIRE(lh && out && world >= 2 && world <= kPeerMaxWorld, "peer layout arguments");
   Learner* l = reinterpret_cast<Learner*>(lh);

@@ -180,3 +180,27 @@ def test_data_parallel_gradient_mean_equals_global_batch():
         for k in full.files:
             assert np.allclose(r0[k], r1[k], rtol=0, atol=0), k             # replicas stay identical
             assert np.allclose(r0[k], full[k], rtol=1e-9, atol=1e-12), k   # and equal the global-batch learner
+
+
+def test_peer_exchange_layout_is_aligned_and_disjoint():
+    """Data-parallel gradient exchange buffer (csrc/peer.cuh): [flags | critic grads | actor grads | critic sums | actor
+    sums]; every block padded so that each of `world` ranks owns a whole number of float4, 256-byte aligned, disjoint."""
+    from ctypes import byref
+    from r2d2_b200 import native
+    lib = native.lib()
+    n_critic, n_actor = 2311697, 1381393          # odd sizes on purpose
+    for world in (2, 3, 4, 8, 16):
+        lay = native.PeerLayout()
+        native.check(lib.r2d2_peer_layout_for(n_critic, n_actor, world, byref(lay)))
+        q = 4 * world
+        pad_c, pad_a = -(-n_critic // q) * q, -(-n_actor // q) * q
+        blocks = [(lay.off_critic_grads, pad_c), (lay.off_actor_grads, pad_a), (lay.off_critic_sums, pad_c),
+                  (lay.off_actor_sums, pad_a)]
+        end = 4096                                 # the flag area
+        for off, n in blocks:
+            assert off % 256 == 0 and off >= end
+            end = off + 4 * n
+        assert lay.bytes >= end and lay.bytes % 256 == 0
+    lay = native.PeerLayout()
+    assert lib.r2d2_peer_layout_for(n_critic, n_actor, 1, byref(lay)) != 0      # one rank has nothing to exchange
+    assert lib.r2d2_peer_layout_for(n_critic, n_actor, 17, byref(lay)) != 0
