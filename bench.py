@@ -281,6 +281,7 @@ class Arm:
         self.eng.step(prefetch=self._next_batch)
 
     def time_resident(self, steps, warmup, barrier, clocks=None):
+        self.eng.discard_prefetched()
         self.rp.sample_into(self.eng, generator=self.gen)     # batch 0; every step draws its successor
         for _ in range(warmup):
             self.step_resident()
@@ -305,6 +306,7 @@ class Arm:
         a stream synchronisation (learner.py:135).  The host batch overwrites the device-gathered one, so the timed
         region contains both the device sampler work and the host->device traffic of the same bytes."""
         eng, rp = self.eng, self.rp
+        eng.discard_prefetched()
         B = self.cfg.batch
         n_pool = 3
         pool = []

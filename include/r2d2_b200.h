@@ -246,6 +246,8 @@ int r2d2_learner_buffers_get(r2d2_learner_t* l, r2d2_learner_buffers* out);
 int r2d2_learner_buffers_get_slot(r2d2_learner_t* l, int slot, r2d2_learner_buffers* out);
 int r2d2_learner_select_batch(r2d2_learner_t* l, int slot);
 int r2d2_learner_target_phase(r2d2_learner_t* l, int slot, r2d2_stream_t stream);
+/* forget a target phase that ran ahead: the caller is about to overwrite that slot's batch */
+int r2d2_learner_discard_prefetch(r2d2_learner_t* l, r2d2_stream_t stream);
 /* phase 1: target chains (unless r2d2_learner_target_phase already ran for the selected slot), online critic chain,
  * TD/priority kernel, critic BPTT -> critic_grads */
 int r2d2_learner_critic_phase(r2d2_learner_t* l, r2d2_stream_t stream);

@@ -237,6 +237,10 @@ int r2d2_learner_target_phase(r2d2_learner_t* l, int slot, r2d2_stream_t stream)
   R2D2_REQUIRE(l, "null");
   return learner_target_phase(reinterpret_cast<Learner*>(l), slot, S(stream));
 }
+int r2d2_learner_discard_prefetch(r2d2_learner_t* l, r2d2_stream_t stream) {
+  R2D2_REQUIRE(l, "null");
+  return learner_discard_prefetch(reinterpret_cast<Learner*>(l), S(stream));
+}
 int r2d2_learner_critic_phase(r2d2_learner_t* l, r2d2_stream_t stream) {
   R2D2_REQUIRE(l, "null");
   return learner_critic_phase(reinterpret_cast<Learner*>(l), S(stream));

@@ -110,6 +110,15 @@ int learner_select_batch(Learner* l, int slot) {
   return R2D2_OK;
 }
 
+int learner_discard_prefetch(Learner* l, cudaStream_t st) {
+  R2D2_REQUIRE(l, "null");
+  // whatever the side stream still writes into the online critic's workspace for the dropped batch goes first
+  if (l->c1_inputs_slot >= 0 && l->side) R2D2_CUDA_TRY(cudaStreamWaitEvent(st, l->ev_c1_inputs, 0));
+  l->c1_inputs_slot = -1;
+  l->targets_slot = -1;
+  return R2D2_OK;
+}
+
 int learner_target_phase(Learner* l, int slot, cudaStream_t st) {
   R2D2_REQUIRE(l && (slot == 0 || slot == 1), "batch slot");
   const r2d2_learner_config& c = l->cfg;

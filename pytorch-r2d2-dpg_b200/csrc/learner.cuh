@@ -56,6 +56,8 @@ int learner_select_batch(Learner* l, int slot);
 // target chains of the batch in `slot` (learner.py:87,94-95,106): q_next for the next learner_critic_phase on that slot.
 // Reads the target nets and the batch only.  learner_critic_phase runs it itself when the current slot has none.
 int learner_target_phase(Learner* l, int slot, cudaStream_t stream);
+// forget a target phase that ran ahead (the caller is about to overwrite that batch)
+int learner_discard_prefetch(Learner* l, cudaStream_t stream);
 int learner_critic_phase(Learner* l, cudaStream_t stream);
 int learner_actor_forward(Learner* l, cudaStream_t stream);
 int learner_actor_phase(Learner* l, float grad_scale, cudaStream_t stream);

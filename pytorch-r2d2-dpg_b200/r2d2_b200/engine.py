@@ -126,6 +126,7 @@ class LearnerEngine:
                                 "leaf_idx": nv.view_i64(b.leaf_idx, (B,), dev),
                                 "uniforms": nv.view_f32(b.uniforms, (B,), dev)})
         self._lib_slot = 0
+        self._targets_ahead = False      # the fill slot's target chains already ran: its batch must not change any more
         self._bind_slot(0)
         self.q_value = nv.view_f32(b.q_value, (L * B, A), dev)
         self.target_q_value = nv.view_f32(b.target_q_value, (L * B, A), dev)
@@ -145,6 +146,17 @@ class LearnerEngine:
         self._peer_hdl = None
         self._pending_finish = False
         self._sync_actor = None
+
+    def _guard_fill(self):
+        if self._targets_ahead:
+            raise nv.NativeError("the engine's batch was filled by a step(prefetch=...) hook and its target chains "
+                                 "have already run: call step(), or discard_prefetched(), before writing another batch")
+
+    def discard_prefetched(self):
+        """Drop a batch that a step(prefetch=...) hook drew ahead (its target chains are forgotten too): the next
+        sample_into / set_batch starts a fresh sequence."""
+        nv.check(self.lib.r2d2_learner_discard_prefetch(self._h, nv.current_stream()))
+        self._targets_ahead = False
 
     def _bind_slot(self, slot: int):
         for k, v in self._slots[slot].items():
@@ -277,6 +289,7 @@ class LearnerEngine:
         """Copy an already sampled time-major batch (replay_memory.py:123-136 layout) into the engine."""
         cv = lambda x: torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x,  # noqa: E731
                                        dtype=torch.float32).to(self.device, non_blocking=True)
+        self._guard_fill()
         self.obs.copy_(cv(batch["obs"]))
         self.act.copy_(cv(batch["act"]))
         self.rew.copy_(cv(batch["rew"]).reshape(self.rew.shape))
@@ -306,6 +319,7 @@ class LearnerEngine:
         if self._fill_slot != self._lib_slot:
             nv.check(self.lib.r2d2_learner_select_batch(self._h, self._fill_slot))
             self._lib_slot = self._fill_slot
+        self._targets_ahead = False
         if self._pending_finish and self._finish_updates_targets():
             self.flush()                                                  # the target chains below read the target nets
         nv.check(self.lib.r2d2_learner_critic_phase(self._h, s))
@@ -316,6 +330,7 @@ class LearnerEngine:
             if ahead:
                 self._run_prefetch(prefetch)
                 nv.check(self.lib.r2d2_learner_target_phase(self._h, self._fill_slot, s))
+                self._targets_ahead = True
             nv.check(self.lib.r2d2_learner_actor_forward(self._h, s))
             nv.check(self.lib.r2d2_learner_actor_phase(self._h, scale, s))
             if mode == "peer":   # signal / slice-sum / wait kernels are issued by the phases themselves
@@ -475,6 +490,7 @@ class DeviceReplay:
     def sample_into(self, eng: LearnerEngine, generator: torch.Generator | None = None, u: torch.Tensor | None = None):
         """Draw eng.cfg.batch starts and gather the time-major batch straight into the engine's buffers."""
         ec, rc = eng.cfg, self.cfg
+        eng._guard_fill()
         if (ec.obs, ec.act, ec.hidden, ec.rows) != (rc.obs, rc.act, rc.hidden, rc.rows):
             raise nv.NativeError("replay shard (obs %d act %d hidden %d rows %d) does not match the engine (obs %d act %d "
                                  "hidden %d rows %d)" % (rc.obs, rc.act, rc.hidden, rc.rows, ec.obs, ec.act, ec.hidden, ec.rows))

@@ -123,6 +123,7 @@ SIGNATURES = {
     "r2d2_learner_buffers_get_slot": (c_int, [c_void_p, c_int, POINTER(LearnerBuffers)]),
     "r2d2_learner_select_batch": (c_int, [c_void_p, c_int]),
     "r2d2_learner_target_phase": (c_int, [c_void_p, c_int, c_void_p]),
+    "r2d2_learner_discard_prefetch": (c_int, [c_void_p, c_void_p]),
     "r2d2_peer_layout_for": (c_int, [c_longlong, c_longlong, c_int, POINTER(PeerLayout)]),
     "r2d2_learner_peer_layout": (c_int, [c_void_p, c_int, POINTER(PeerLayout)]),
     "r2d2_learner_attach_peers": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),

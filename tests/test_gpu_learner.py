@@ -285,3 +285,12 @@ def test_pipelined_step_matches_sequential(eng_mod, hidden, batch):
     for net in ("actor", "critic", "target_actor", "target_critic"):
         assert rel_l2(pip.flat[net].cpu().numpy(), seq.flat[net].cpu().numpy()) < 1e-5, net
     assert pip.launches_per_iteration == seq.launches_per_iteration
+    with pytest.raises(Exception, match="target chains"):       # the prefetched batch is final until the next step
+        pip.set_batch(batches[0])
+    pip.discard_prefetched()
+    for e in (seq, pip):                                        # ... or explicitly dropped: both engines continue alike
+        e.set_batch(batches[1])
+        e.step()
+    torch.cuda.synchronize()
+    for net in ("actor", "critic"):
+        assert rel_l2(pip.flat[net].cpu().numpy(), seq.flat[net].cpu().numpy()) < 1e-5, net

@@ -40,6 +40,7 @@ def run(variant):
         if eng._fill_slot != eng._lib_slot:
             nv.check(lib.r2d2_learner_select_batch(eng._h, eng._fill_slot))
             eng._lib_slot = eng._fill_slot
+        eng._targets_ahead = False
         if eng._pending_finish and eng._finish_updates_targets():
             eng.flush()
         nv.check(lib.r2d2_learner_critic_phase(eng._h, s)); rec(1)
