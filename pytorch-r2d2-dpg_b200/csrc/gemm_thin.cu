@@ -8,6 +8,8 @@
 //   thin_smalln : C[M,N] = epi(A[M,K] W + bias),                  N <= 32        (NT / NN)
 //   thin_tn     : C[M,N] += A[K,M]^T B[K,N],                      M <= 32 or N <= 32, reduction over K rows
 #include "gemm.cuh"
+
+#include <stdlib.h>
 #include "tc05.cuh"
 
 namespace r2d2 {
@@ -309,16 +311,96 @@ __global__ void __launch_bounds__(256) thin_rowdot_kernel(GemmParams p) {
   }
 }
 
+// Second version: the kernel above is bound by the shared-memory pipe - a 128-bit shared load is served one quarter
+// warp per clock and every quarter (= one row) re-reads the same 8 weight pieces, so the [N][K] tile crosses the pipe once
+// per ROW (69 groups x 17 columns x 16 loads x 4 clocks = 75 k clocks = 40 us per SM of the 70 us at cfg-3).  Here all 32
+// lanes share one k-slice layout (lane j holds the 16-byte pieces j, j + 32, ... of each of the warp's FOUR rows), so a
+// weight load feeds four rows: the tile crosses the pipe once per four rows.  The 4 x 32 partial sums are reduced with a
+// transposing butterfly: 2 + 1 exchanges halve the rows per lane, 3 more add the 8 lanes of a row (6 shuffles per column).
+template <bool NN, int KI>   // KI = K / 32; K / 128 pieces per lane and row
+__global__ void __launch_bounds__(256, 2) thin_rowdot4_kernel(GemmParams p) {
+  extern __shared__ __align__(16) float Wt[];   // [N][K]
+  constexpr int KQ = KI / 4;
+  static_assert(KI % 4 == 0, "K must be a multiple of 128");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = KI * 32;
+  for (int idx = tid; idx < p.N * K; idx += 256) {
+    int n, k;
+    if (NN) { k = idx / p.N; n = idx % p.N; } else { n = idx / K; k = idx % K; }
+    Wt[n * K + k] = NN ? __ldg(p.B + (long long)k * p.ldb + n) : __ldg(p.B + (long long)n * p.ldb + k);
+  }
+  __syncthreads();
+  const bool needs_z = p.epilogue == EPI_MUL_DTANH || p.epilogue == EPI_ADD_Z;
+  const bool hi = (lane & 16) != 0, b8 = (lane & 8) != 0;
+  const int my_r = (hi ? 2 : 0) + (b8 ? 1 : 0);   // the row of the group whose sums end up in this lane
+  const int groups = (p.M + 3) >> 2;
+  for (int g = blockIdx.x * 8 + warp; g < groups; g += gridDim.x * 8) {
+    float4 a[4][KQ];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = g * 4 + r;
+      const bool on = row < p.M;
+      const float4* arow = reinterpret_cast<const float4*>(p.A + (long long)(on ? row : 0) * p.lda);
+#pragma unroll
+      for (int i = 0; i < KQ; ++i) a[r][i] = on ? __ldg(arow + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int row = g * 4 + my_r;
+    const bool on = row < p.M;
+    for (int n = 0; n < p.N; n += 2) {   // two output columns per pass
+      const int n1 = n + 1 < p.N ? n + 1 : n;
+      const float4* w0 = reinterpret_cast<const float4*>(Wt + n * K);
+      const float4* w1 = reinterpret_cast<const float4*>(Wt + n1 * K);
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < KQ; ++i) {
+        const float4 u = w0[i * 32 + lane], v = w1[i * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          s0[r] = fmaf(a[r][i].w, u.w, fmaf(a[r][i].z, u.z, fmaf(a[r][i].y, u.y, fmaf(a[r][i].x, u.x, s0[r]))));
+          s1[r] = fmaf(a[r][i].w, v.w, fmaf(a[r][i].z, v.z, fmaf(a[r][i].y, v.y, fmaf(a[r][i].x, v.x, s1[r]))));
+        }
+      }
+      // lanes with bit 4 keep rows 2, 3 and hand rows 0, 1 to their partner (and vice versa); then bit 3 picks one row
+      float k0 = hi ? s0[2] : s0[0], k1 = hi ? s0[3] : s0[1];
+      float l0 = hi ? s1[2] : s1[0], l1 = hi ? s1[3] : s1[1];
+      k0 += __shfl_xor_sync(0xffffffffu, hi ? s0[0] : s0[2], 16);
+      k1 += __shfl_xor_sync(0xffffffffu, hi ? s0[1] : s0[3], 16);
+      l0 += __shfl_xor_sync(0xffffffffu, hi ? s1[0] : s1[2], 16);
+      l1 += __shfl_xor_sync(0xffffffffu, hi ? s1[1] : s1[3], 16);
+      float acc0 = (b8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b8 ? k0 : k1, 8);
+      float acc1 = (b8 ? l1 : l0) + __shfl_xor_sync(0xffffffffu, b8 ? l0 : l1, 8);
+#pragma unroll
+      for (int d = 4; d >= 1; d >>= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, d);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, d);
+      }
+      // the 8 lanes that hold a row's sums share the stores: lane (n % 8) of them writes column n
+      const bool first = (n & 7) == (lane & 7), second = n1 != n && (n1 & 7) == (lane & 7);
+      if (on && (first || second)) {
+        const int nn = first ? n : n1;
+        const float acc = first ? acc0 : acc1;
+        const float b = p.bias ? __ldg(p.bias + nn) : 0.f;
+        const float z = needs_z ? p.Z[(long long)row * p.ldz + nn] : 0.f;
+        p.C[(long long)row * p.ldc + nn] = apply_epilogue(acc + b, p.epilogue, z);
+      }
+    }
+  }
+}
+
 template <bool NN, int KI>
 int launch_thin_rowdot(const GemmParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)p.N * KI * 32 * sizeof(float);
+  static const bool v1 = [] { const char* e = getenv("R2D2_ROWDOT_V1"); return e && e[0] == '1'; }();   // dev A/B
   static PerDeviceOnce once;
-  if (smem > 48 * 1024 && once.need())
+  if (smem > 48 * 1024 && once.need()) {
     R2D2_CUDA_TRY(cudaFuncSetAttribute(thin_rowdot_kernel<NN, KI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    R2D2_CUDA_TRY(cudaFuncSetAttribute(thin_rowdot4_kernel<NN, KI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  }
   const int groups = ceil_div(p.M, 4);
   int grid = ceil_div(groups, 8);
   if (grid > 148 * 4) grid = 148 * 4;
-  thin_rowdot_kernel<NN, KI><<<grid, 256, smem, stream>>>(p);
+  if (v1) thin_rowdot_kernel<NN, KI><<<grid, 256, smem, stream>>>(p);
+  else thin_rowdot4_kernel<NN, KI><<<grid, 256, smem, stream>>>(p);
   count_launch();
   R2D2_CUDA_TRY(cudaGetLastError());
   return R2D2_OK;
