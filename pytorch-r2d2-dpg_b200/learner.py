@@ -11,7 +11,8 @@ so the reference's r2d2.py launcher runs unchanged - while every iteration of th
 Data-parallel form: launch `learner_process` once per GPU under torchrun (RANK / LOCAL_RANK /
 WORLD_SIZE in the environment).  `Learner.__init__` then binds cuda:LOCAL_RANK, joins the NCCL process group,
 ingests only the actors i with i mod WORLD_SIZE == RANK into its own HBM replay shard, and the two flat
-gradient blocks are all-reduced at the optimiser steps; rank 0 alone writes model.pt.  Nothing else crosses GPUs.
+gradient blocks are summed over the ranks by the library's peer-memory kernels inside the iteration (csrc/peer.cu);
+rank 0 alone writes model.pt.  Nothing else crosses GPUs.
 """
 import os
 from time import sleep, time
@@ -111,6 +112,7 @@ class Learner:
 
     def update_target_model(self):
         self.engine.flush()
+        self.engine.discard_prefetched()      # target chains that already ran for the next batch used the old target nets
         self.engine.flat['target_actor'].copy_(self.engine.flat['actor'])
         self.engine.flat['target_critic'].copy_(self.engine.flat['critic'])
 
@@ -125,34 +127,17 @@ class Learner:
             sleep(0.1)
             if self.dist_env.is_main:
                 print('learner memory sequence size:', self.memory.sequence_counter)
-        step = 0
-        dev = self.memory._dev
+        from r2d2_b200.run_loop import run_learner_loop
 
-        def next_batch(eng, used):
-            # priorities of the batch just trained on (learner.py:135-139), then the next draw (learner.py:84): the
-            # engine calls this as soon as the priorities exist and runs the next batch's target chains mid-iteration
-            dev.update_priorities(used.leaf_idx, used.priority)
-            dev.sample_into(eng)
+        def save():
+            self.save_model()
+            if os.environ.get("R2D2_SAVE_STATE", "1") == "1":
+                self.save_checkpoint()
 
-        have_batch = False
-        while max_steps is None or step < max_steps:
-            if step % 100 == 0 and self.dist_env.is_main:
+        def log(step):
+            if self.dist_env.is_main:
                 print('learning step:', step)
-            step += 1
-            if not have_batch:
-                dev.sample_into(self.engine)                           # learner.py:84
-            if step % self.memory_update_interval == 0 or step == max_steps:
-                # an ingest follows this step: it may evict rows, so no batch is drawn ahead of it
-                self.engine.step()                                     # learner.py:86-132
-                dev.update_priorities(self.engine.leaf_idx, self.engine.priority)   # learner.py:135-139
-                have_batch = False
-            else:
-                self.engine.step(prefetch=next_batch)
-                have_batch = True
-            if step % self.model_save_interval == 0:
-                self.save_model()
-                if os.environ.get("R2D2_SAVE_STATE", "1") == "1":
-                    self.save_checkpoint()
-            if step % self.memory_update_interval == 0:
-                self._ingest()                                         # learner.py:144-149 without the sleep stall
+
+        run_learner_loop(self.engine, self.memory._dev, max_steps=max_steps, ingest_every=self.memory_update_interval,
+                         save_every=self.model_save_interval, ingest=self._ingest, save=save, log=log)
         torch.cuda.synchronize()

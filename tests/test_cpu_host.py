@@ -204,3 +204,72 @@ def test_peer_exchange_layout_is_aligned_and_disjoint():
     lay = native.PeerLayout()
     assert lib.r2d2_peer_layout_for(n_critic, n_actor, 1, byref(lay)) != 0      # one rank has nothing to exchange
     assert lib.r2d2_peer_layout_for(n_critic, n_actor, 17, byref(lay)) != 0
+
+
+class _FakeEngine:
+    """Records what run_learner_loop does.  Mimics LearnerEngine.step: the prefetch hook runs once per step, after the
+    priorities of the current batch exist; the attributes leaf_idx / priority describe the batch in the engine."""
+
+    def __init__(self, log):
+        self.log, self.batch, self.leaf_idx, self.priority = log, None, None, None
+
+    def step(self, prefetch=None):
+        assert self.batch is not None, "step without a batch"
+        trained = self.batch
+        self.log.append(("step", trained, prefetch is not None))
+        self.leaf_idx, self.priority = ("leaf", trained), ("prio", trained)
+        if prefetch is not None:
+            from types import SimpleNamespace
+            used = SimpleNamespace(leaf_idx=self.leaf_idx, priority=self.priority)
+            self.batch = None
+            prefetch(self, used)
+        else:
+            self.batch = ("consumed", trained)
+
+
+class _FakeReplay:
+    def __init__(self, log):
+        self.log, self.draws = log, 0
+
+    def sample_into(self, eng):
+        self.draws += 1
+        eng.batch = self.draws
+        self.log.append(("draw", self.draws))
+
+    def update_priorities(self, leaf_idx, priority):
+        assert leaf_idx[1] == priority[1]
+        self.log.append(("writeback", leaf_idx[1]))
+
+
+@pytest.mark.parametrize("max_steps,ingest_every,save_every", [(23, 5, 4), (10, 1, 3), (7, 50, 50), (12, 4, 4)])
+def test_run_loop_keeps_the_sequential_data_flow(max_steps, ingest_every, save_every):
+    """Host logic of Learner.run (r2d2_b200/run_loop.py): every batch is trained on once, its priorities are written
+    back exactly once and before the next draw, nothing is drawn ahead of an ingest, saves / ingests fall on the
+    reference's steps (learner.py:141-149)."""
+    from r2d2_b200.run_loop import run_learner_loop
+    log = []
+    eng, rp = _FakeEngine(log), _FakeReplay(log)
+    n = run_learner_loop(eng, rp, max_steps=max_steps, ingest_every=ingest_every, save_every=save_every,
+                         ingest=lambda: log.append(("ingest",)), save=lambda: log.append(("save",)),
+                         log=lambda s: log.append(("log", s)), log_every=5)
+    assert n == max_steps
+    steps = [e for e in log if e[0] == "step"]
+    assert [e[1] for e in steps] == list(range(1, max_steps + 1))            # batch k is trained on in step k, once
+    assert [e[1] for e in log if e[0] == "writeback"] == list(range(1, max_steps + 1))
+    assert [e[1] for e in log if e[0] == "draw"] == list(range(1, max_steps + 1))   # no batch drawn and dropped
+    pos = {e: i for i, e in enumerate(log)}
+    for k in range(1, max_steps):
+        assert pos[("writeback", k)] < pos[("draw", k + 1)]                  # tree is up to date for the next draw
+    # ingests: after the steps that are multiples of ingest_every, and no batch is in flight across them
+    ingest_at = [i for i, e in enumerate(log) if e[0] == "ingest"]
+    assert len(ingest_at) == max_steps // ingest_every
+    for i in ingest_at:
+        done = [e[1] for e in log[:i] if e[0] == "step"]
+        assert done and done[-1] % ingest_every == 0
+        drawn = [e[1] for e in log[:i] if e[0] == "draw"]
+        assert drawn[-1] == done[-1], "a batch was drawn ahead of an ingest"
+    assert len([e for e in log if e[0] == "save"]) == max_steps // save_every
+    # the steps in front of an ingest and the last one are sequential, all others hand the hook to the engine
+    for _, k, pipelined in steps:
+        assert pipelined == (k % ingest_every != 0 and k != max_steps)
+    assert [e[1] for e in log if e[0] == "log"] == list(range(0, max_steps, 5))
