@@ -204,9 +204,10 @@ class LearnerEngine:
         put("target_critic", target_critic if target_critic is not None else critic)
 
     def enable_data_parallel(self, require: bool | None = None):
-        """Gradients are averaged over ranks at the two optimiser steps (NCCL all-reduce of the flat buffers on a
-        side stream; the critic's overlaps with the actor's forward chain).  `require` (default: WORLD_SIZE > 1 in the
-        environment) turns a missing process group into an error instead of N silently independent learners."""
+        """Gradients are averaged over ranks at the two optimiser steps: by the library's own kernels over NVLink peer
+        memory (`_attach_peers`, csrc/peer.cu), or - fallback / R2D2_DP_MODE=defer - by NCCL all-reduces of the flat
+        buffers on a side stream.  `require` (default: WORLD_SIZE > 1 in the environment) turns a missing process group
+        into an error instead of N silently independent learners."""
         import os
         import torch.distributed as dist
         from .dist_env import GradSync
@@ -312,7 +313,8 @@ class LearnerEngine:
 
         Data parallel, mode "peer" (default): the gradient blocks are summed by the library's own kernels over NVLink
         peer memory inside the phases (csrc/peer.cuh); the actor's optimiser step of iteration i runs after the critic
-        phase of iteration i+1.  Mode "defer": the same schedule with NCCL all-reduces on a side stream."""
+        phase of iteration i+1.  Mode "defer" (fallback): NCCL all-reduces on a side stream, the actor's waited for
+        after the next critic phase; the hook then runs at the end of the step."""
         s = nv.current_stream()
         scale = 1.0 / self.world
         mode = self._dp_mode if self._dist is not None else "single"
