@@ -273,3 +273,28 @@ def test_run_loop_keeps_the_sequential_data_flow(max_steps, ingest_every, save_e
     for _, k, pipelined in steps:
         assert pipelined == (k % ingest_every != 0 and k != max_steps)
     assert [e[1] for e in log if e[0] == "log"] == list(range(0, max_steps, 5))
+
+
+def test_bench_configs_are_the_baseline_configs():
+    """bench.py measures BASELINE.json's metric on BASELINE.json's shapes: configs[1] / configs[2] are parsed from the
+    baseline's own strings, the headline (default --config) is configs[2], and both arms print the same workload."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert bench.METRIC.split(" (")[0] in base["metric"]
+
+    def shape(text):
+        kv = dict(re.findall(r"(obs|act|hidden|seq_len|burn_in|batch)=(\d+)", text))
+        return {k: int(v) for k, v in kv.items()}
+
+    for name, idx in (("cfg2", 1), ("cfg3", 2)):
+        want, have = shape(base["configs"][idx]), bench.CONFIGS[name]
+        assert want["obs"] == have["obs"] and want["act"] == have["act"] and want["hidden"] == have["hidden"]
+        assert want["batch"] == have["batch"] and want["seq_len"] == have["learning"]
+        assert want.get("burn_in", have["burn_in"]) == have["burn_in"]
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert re.search(r'add_argument\("--config", default="cfg3"', src)
+    assert src.count("workload_string(name, c)") >= 2          # the B200 arm and the reference arm
+    line = bench.workload_string("cfg3", bench.CONFIGS["cfg3"])
+    assert line == "cfg3: obs=376 act=17 hidden=512 batch=512 burn_in=40 learning=80 n_step=5"
